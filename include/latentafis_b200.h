@@ -1,0 +1,175 @@
+/*
+ * latentafis_b200 — C ABI of the B200-native MSU-LatentAFIS 1-vs-N gallery matcher.
+ *
+ * The reference has no FFI: its in-process surface is the C++ class PQ::Matcher
+ * (matching/matcher.h:34-75) driven by matching/main.cpp.  This header is the C-ABI equivalent of
+ * that surface for the hot path; every entry point names the reference member it
+ * replaces.  Plain pointers and sizes only; no torch / CUDA types.  All functions return an
+ * LAFIS_* status; lafis_last_error() gives a human-readable message for the last failure on a
+ * context.  A context may be used from one host thread at a time.  The library requires a CUDA
+ * device of compute capability 10.x; there is no CPU fallback — every entry point that computes
+ * fails with LAFIS_ERR_CUDA when the device path is unavailable.
+ */
+#ifndef LATENTAFIS_B200_H
+#define LATENTAFIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAFIS_API __attribute__((visibility("default")))
+
+/* ---- status codes.  Positive values mirror the reference's own return conventions
+ *      (matcher.cpp:296-299 driver "latent empty" = 1; loaders :798-801, :837-846, :865-869). ---- */
+enum {
+    LAFIS_OK = 0,
+    LAFIS_LATENT_EMPTY = 1,        /* One2List_matching returns 1: latent has nothing to match with */
+    LAFIS_ERR_NO_TEMPLATES = -1,   /* drivers return -1 when a directory holds no *.dat */
+    LAFIS_ERR_ARG = -2,
+    LAFIS_ERR_IO = -3,
+    LAFIS_ERR_CODEBOOK = -4,       /* not a 16 x 256 x 6 codebook */
+    LAFIS_ERR_CUDA = -5,
+    LAFIS_ERR_UNSUPPORTED_SIZE = -6, /* template larger than the device kernels are built for */
+    LAFIS_ERR_LATENT_LAYOUT = -7,  /* score[28] would be read out of bounds by the reference
+                                      (matcher.cpp:188): latent has < 29 template slots */
+    LAFIS_ERR_NO_GALLERY = -8
+};
+
+/* per-template load status kept for every gallery entry (matcher.cpp:886-983 return values) */
+enum {
+    LAFIS_TPL_OK = 0,
+    LAFIS_TPL_EMPTY = 1,      /* file <= 10 bytes, or nothing usable inside: score stays -1 */
+    LAFIS_TPL_TRUNCATED = 2,  /* loader returned 2 or 4 part-way: templates read so far are kept */
+    LAFIS_TPL_FAILED = -1     /* loader returned < 0: the drivers empty the template, score -1 */
+};
+
+typedef struct lafis_ctx lafis_ctx;
+
+/* one rank-list entry; ordering is (score descending, gallery index ascending) */
+typedef struct {
+    float score;
+    uint32_t index; /* global gallery index (shard base + local index) */
+} lafis_hit;
+
+/* A gallery in structure-of-arrays form, host or device memory.  Template g owns minutiae
+ * [minu_off[g], minu_off[g+1]) and texture points [tex_off[g], tex_off[g+1]).  Descriptors are
+ * row-major as in the .dat files (matcher.cpp:948-953, :971-975); the library re-lays them out for
+ * the kernels.  Texture point counts above 1000 are truncated like matcher.cpp:546-547. */
+typedef struct {
+    int32_t n_templates;
+    const uint32_t* minu_off;  /* [n_templates+1] */
+    const int16_t* minu_x;     /* pixels */
+    const int16_t* minu_y;
+    const float* minu_ori;
+    const float* minu_des;     /* [total_minu][96] */
+    const uint32_t* tex_off;   /* [n_templates+1] */
+    const int16_t* tex_x;      /* block units */
+    const int16_t* tex_y;
+    const float* tex_ori;
+    const uint8_t* tex_codes;  /* [total_tex][16] */
+    const int8_t* status;      /* [n_templates] LAFIS_TPL_*, may be NULL (= all OK) */
+    int32_t on_device;         /* 0: host pointers; 1: device pointers on the context's GPU
+                                  (minu_off / tex_off / status are always host pointers) */
+} lafis_packed_gallery;
+
+/* A batch of latent prints, host memory.  Only what the matcher reads is carried: the three
+ * selected minutiae templates {26, 2, 11} (matcher.cpp:380) and texture template 0 (:411).
+ * Slot s of latent q owns minutiae [minu_off[3q+s], minu_off[3q+s+1]). */
+typedef struct {
+    int32_t n_latents;
+    const int32_t* n_minu_templates; /* [n] non-empty minutiae templates in the file (28 expected) */
+    const int32_t* n_tex_templates;  /* [n] */
+    const uint32_t* minu_off;        /* [3n+1] */
+    const int16_t* minu_x;
+    const int16_t* minu_y;
+    const float* minu_ori;
+    const float* minu_des;           /* [total][96] */
+    const uint32_t* tex_off;         /* [n+1] */
+    const int16_t* tex_x;
+    const int16_t* tex_y;
+    const float* tex_ori;
+    const float* tex_des;            /* [total][96] */
+} lafis_packed_latents;
+
+/* ---- context: replaces PQ::Matcher::Matcher(code_file), matcher.cpp:31-94 ---- */
+LAFIS_API int lafis_create(const char* codebook_path, int device, lafis_ctx** out);
+/* same, from an in-memory 16 x 256 x 6 float codebook */
+LAFIS_API int lafis_create_from_codebook(const float* codewords, int subs, int clusters, int sub_dim, int device,
+                                         lafis_ctx** out);
+LAFIS_API void lafis_destroy(lafis_ctx* ctx);
+LAFIS_API const char* lafis_last_error(const lafis_ctx* ctx);
+LAFIS_API const char* lafis_version(void);
+
+/* ---- gallery ingest: replaces the per-pair load_FP_template(rolled) inside the hot loop,
+ *      matcher.cpp:173 / :278 / :886-983.  The gallery stays resident in HBM across matches.
+ *      shard_rank / shard_count select a contiguous slice [floor(G*r/c), floor(G*(r+1)/c)) of
+ *      the template list for multi-GPU runs; indices reported in hits stay global. ---- */
+LAFIS_API int lafis_gallery_load_dir(lafis_ctx* ctx, const char* dir, int shard_rank, int shard_count);
+LAFIS_API int lafis_gallery_load_files(lafis_ctx* ctx, const char* const* paths, int n, int shard_rank,
+                                       int shard_count);
+LAFIS_API int lafis_gallery_set_packed(lafis_ctx* ctx, const lafis_packed_gallery* g, uint32_t index_base);
+LAFIS_API int lafis_gallery_size(const lafis_ctx* ctx);          /* templates resident on this context */
+LAFIS_API const char* lafis_gallery_path(const lafis_ctx* ctx, int local_index); /* "" for packed input */
+LAFIS_API int lafis_gallery_status(const lafis_ctx* ctx, int local_index);
+LAFIS_API uint64_t lafis_gallery_bytes(const lafis_ctx* ctx);    /* algorithmic bytes resident (392*nRm + 24*nRt) */
+
+/* read one resident template back in .dat form (tests / oracle sampling); arrays may be NULL to
+ * query the counts only.  des is row-major [n_minu][96], codes [n_tex][16]. */
+LAFIS_API int lafis_gallery_get_template(const lafis_ctx* ctx, int local_index, int* n_minu, int16_t* mx, int16_t* my,
+                                         float* mori, float* mdes, int* n_tex, int16_t* tx, int16_t* ty, float* tori,
+                                         uint8_t* tcodes);
+
+/* ---- latent parsing: replaces load_FP_template(latent), matcher.cpp:785-884 (without the LUT,
+ *      which the device builds).  The returned handle owns a host-side packed batch. ---- */
+typedef struct lafis_latents lafis_latents;
+LAFIS_API int lafis_latents_load_files(lafis_ctx* ctx, const char* const* paths, int n, lafis_latents** out);
+LAFIS_API int lafis_latents_from_packed(lafis_ctx* ctx, const lafis_packed_latents* p, lafis_latents** out);
+LAFIS_API int lafis_latents_count(const lafis_latents* l);
+LAFIS_API int lafis_latents_status(const lafis_latents* l, int q); /* LAFIS_OK, LAFIS_LATENT_EMPTY, LAFIS_ERR_LATENT_LAYOUT */
+LAFIS_API void lafis_latents_free(lafis_latents* l);
+/* pre-stage the batch in HBM so that a following lafis_match() performs no host-to-device copy */
+LAFIS_API int lafis_latents_make_resident(lafis_ctx* ctx, lafis_latents* l);
+
+/* ---- the hot path: replaces the omp loop of One2List_matching / List2List_matching
+ *      (matcher.cpp:168-190, :273-295) = One2One_matching_selected_templates (:376-417) for every
+ *      (latent, gallery[i]) plus the fusion of :188, followed by the rank list of :306-309.
+ *
+ *      all_scores : optional [n_latents * gallery_size] fused scores, -1 where the reference
+ *                   leaves the slot untouched; host memory.
+ *      components : optional [n_latents * gallery_size * 4] = score[0], score[1], score[2], score[28].
+ *      hits       : optional [n_latents * topk] rank lists of this shard; entries beyond the
+ *                   gallery size are {-inf, UINT32_MAX}.
+ *      Latents whose status is not LAFIS_OK get all_scores = -1 and empty hit lists. ---- */
+LAFIS_API int lafis_match(lafis_ctx* ctx, lafis_latents* latents, int topk, lafis_hit* hits, float* all_scores,
+                          float* components);
+/* same computation, results left in HBM (device-resident timing / multi-GPU gather).  The
+ * returned device pointers stay valid until the next match on this context. */
+LAFIS_API int lafis_match_device(lafis_ctx* ctx, lafis_latents* latents, int topk, const void** d_hits,
+                                 const float** d_all_scores);
+/* merge per-shard rank lists (n_lists lists of topk entries per latent, concatenated per latent)
+ * into global ones with the (score desc, index asc) rule; host memory. */
+LAFIS_API int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n_lists, int topk, lafis_hit* out);
+
+/* ---- enrollment helper: PQ-encode descriptors with the context's codebook,
+ *      TrainedPQEncoder.encode_multi, extraction/descriptor_PQ.py:19-27.  des/codes are device
+ *      pointers when on_device != 0. ---- */
+LAFIS_API int lafis_pq_encode(lafis_ctx* ctx, const float* des, int64_t n, uint8_t* codes, int on_device);
+
+/* ---- instrumentation ---- */
+typedef struct {
+    uint64_t kernel_launches; /* kernels launched by this library since the context was created */
+    uint64_t pairs_scored;    /* (latent, gallery) pairs scored */
+    float last_match_ms;      /* device time of the last lafis_match*, CUDA events */
+    float last_stage_ms[8];   /* per-stage device times of the last match when LAFIS_PROFILE=1:
+                                 0 tex_rowmax, 1 minu_corr, 2 graph_minu, 3 graph_tex, 4 fuse+topk */
+} lafis_stats;
+LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
+LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATENTAFIS_B200_H */

@@ -1,0 +1,54 @@
+// Readers for the matcher's on-disk formats: template .dat files and the PQ codebook.
+// Behavioural mirror of PQ::Matcher::load_FP_template (matching/matcher.cpp:785-884 latent,
+// :886-983 rolled) and of the codebook read in PQ::Matcher::Matcher (:58-93).  Only what the
+// matcher later reads is retained: for a rolled print the first non-empty minutiae
+// template and the first non-empty texture template (matcher.cpp:406, :413 use index 0 only); for a
+// latent print the non-empty minutiae templates at positions 26, 2, 11 (:380) and texture
+// template 0 (:411).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace lafis {
+
+constexpr int kDesLen = 96;        // descriptor length the matcher is built for
+constexpr int kSubs = 16;          // PQ sub-quantizers
+constexpr int kClusters = 256;     // centroids per sub-quantizer
+constexpr int kSubDim = 6;
+constexpr int kMaxMinutiae = 2000; // matcher.cpp:788 / :889 Max_Nrof_Minutiae
+constexpr int kMaxTexture = 1000;  // matcher.h:31-32, applied at matcher.cpp:544-547
+constexpr int kSelected[3] = {26, 2, 11};  // matcher.cpp:380
+
+struct PointSet {
+    std::vector<int16_t> x, y;
+    std::vector<float> ori;
+    std::vector<float> des;     // [n][96] (minutiae, latent texture)
+    std::vector<uint8_t> codes; // [n][16] (rolled texture)
+    int n() const { return (int)x.size(); }
+};
+
+struct RolledTemplate {
+    int status = 0;  // LAFIS_TPL_*
+    int n_minu_templates = 0, n_tex_templates = 0;
+    PointSet minu, tex;
+};
+
+struct LatentTemplate {
+    int load_rc = 0;  // what the reference loader would have returned
+    int n_minu_templates = 0, n_tex_templates = 0;
+    PointSet minu[3];  // slots for template positions 26, 2, 11
+    PointSet tex;
+};
+
+// Returns the reference loader's return code (0, 1, 2, 4, -1) and fills `out`; -3 on I/O error.
+int read_rolled_dat(const std::string& path, RolledTemplate& out);
+int read_latent_dat(const std::string& path, LatentTemplate& out);
+
+// u16 subs, u16 clusters, u16 sub_dim, f32[subs][clusters][sub_dim]; returns 0 or a negative LAFIS_ERR_*
+int read_codebook(const std::string& path, std::vector<float>& codewords, int& subs, int& clusters, int& sub_dim);
+
+// *.dat entries of a directory in directory-iteration order (matcher.cpp:103-110, :122-130, :227-234)
+std::vector<std::string> list_dat_files(const std::string& dir);
+
+}  // namespace lafis

@@ -1,0 +1,204 @@
+// Score fusion, rank-list selection, PQ encoding and gallery re-layout kernels.
+//
+//   reference: score fusion                      matching/matcher.cpp:188 / :293            (K10)
+//              rank list                         matching/matcher.cpp:306-309               (K11)
+//              TrainedPQEncoder.encode_multi     extraction/descriptor_PQ.py:19-27          (§8f.3)
+#pragma once
+#include <math_constants.h>
+
+#include "device_common.cuh"
+
+namespace lafis {
+
+// ---- K10: final = score[0] + score[1] + score[2] + score[28]*0.3 -------------------------------
+// The three float additions happen in float, "score[28]*0.3" and the last addition in double
+// (0.3 is a double literal), the result is narrowed to float.  Slots the reference never writes
+// keep -1: latent not matchable (One2One_matching_selected_templates returns 1) or rolled template
+// empty / failed to load (returns 2, matcher.cpp:173-177, :184-187).
+struct FuseParams {
+    const float* comp;         // [Q][G][4]
+    const int* lat_status;     // [Q]
+    const int* tex_weighted;   // [Q]
+    const int8_t* gal_status;  // [G]
+    int Q, G;
+    float* final_scores;       // [Q][G]
+};
+
+__global__ void fuse_kernel(FuseParams P) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)P.Q * P.G) return;
+    const int q = (int)(e / P.G), g = (int)(e % P.G);
+    float out = -1.0f;
+    const int8_t gs = P.gal_status[g];
+    if (P.lat_status[q] == 0 && (gs == 0 || gs == 2)) {
+        const float4 c = *reinterpret_cast<const float4*>(P.comp + e * 4);
+        const float s012 = f_add(f_add(c.x, c.y), c.z);
+        const float s28 = P.tex_weighted[q] ? c.w : 0.0f;
+        out = (float)((double)s012 + (double)s28 * 0.3);
+    }
+    P.final_scores[e] = out;
+}
+
+// ---- K11: rank lists -----------------------------------------------------------------------------
+// Rank order is (score descending, gallery index ascending) on the unrounded fp32 scores
+// (SURVEY.md §8d).  Both are folded into one 64-bit key whose unsigned order is the rank order.
+__device__ __forceinline__ unsigned long long rank_key(float score, uint32_t index) {
+    uint32_t u = __float_as_uint(score);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(~index);
+}
+__device__ __forceinline__ void rank_unkey(unsigned long long k, float* score, uint32_t* index) {
+    uint32_t u = (uint32_t)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    *score = __uint_as_float(u);
+    *index = ~(uint32_t)(k & 0xffffffffull);
+}
+
+constexpr int kTopkThreads = 512;
+constexpr int kTopkChunk = 4096;
+
+// in-place bitonic sort (descending) of kTopkChunk keys in shared memory
+__device__ __forceinline__ void bitonic_desc(unsigned long long* s) {
+    for (int k = 2; k <= kTopkChunk; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kTopkChunk / 2; t += kTopkThreads) {
+                const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+                const bool desc = ((lo & k) == 0);
+                const unsigned long long a = s[lo], b = s[hi];
+                if ((a < b) == desc) {
+                    s[lo] = b;
+                    s[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// level 0: keys from scores.  grid = (chunks, Q).  out[q][chunk][k]
+__global__ void __launch_bounds__(kTopkThreads) topk_scores_kernel(const float* scores, int G, uint32_t index_base,
+                                                                  int k, unsigned long long* out) {
+    __shared__ unsigned long long s[kTopkChunk];
+    const int q = blockIdx.y, chunk = blockIdx.x;
+    const int base = chunk * kTopkChunk;
+    for (int t = threadIdx.x; t < kTopkChunk; t += kTopkThreads) {
+        const int g = base + t;
+        s[t] = (g < G) ? rank_key(scores[(size_t)q * G + g], index_base + (uint32_t)g) : 0ull;
+    }
+    __syncthreads();
+    bitonic_desc(s);
+    for (int t = threadIdx.x; t < k; t += kTopkThreads) out[((size_t)q * gridDim.x + chunk) * k + t] = s[t];
+}
+
+// level >= 1: keys from keys.  in[q][n_in] -> out[q][chunk][k]
+__global__ void __launch_bounds__(kTopkThreads) topk_keys_kernel(const unsigned long long* in, int n_in, int k,
+                                                                unsigned long long* out) {
+    __shared__ unsigned long long s[kTopkChunk];
+    const int q = blockIdx.y, chunk = blockIdx.x;
+    const int base = chunk * kTopkChunk;
+    for (int t = threadIdx.x; t < kTopkChunk; t += kTopkThreads) {
+        const int g = base + t;
+        s[t] = (g < n_in) ? in[(size_t)q * n_in + g] : 0ull;
+    }
+    __syncthreads();
+    bitonic_desc(s);
+    for (int t = threadIdx.x; t < k; t += kTopkThreads) out[((size_t)q * gridDim.x + chunk) * k + t] = s[t];
+}
+
+struct HitDev {
+    float score;
+    uint32_t index;
+};
+
+__global__ void keys_to_hits_kernel(const unsigned long long* keys, size_t n, HitDev* hits) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned long long k = keys[e];
+    HitDev h;
+    if (k == 0ull) {
+        h.score = -CUDART_INF_F;
+        h.index = 0xffffffffu;
+    } else {
+        rank_unkey(k, &h.score, &h.index);
+    }
+    hits[e] = h;
+}
+
+// ---- PQ encoder ----------------------------------------------------------------------------------
+// One thread per (point, sub-quantizer): nearest of 256 centroids in 6-d, first minimum wins
+// (scipy.cluster.vq.vq).  fp32 squared distances accumulated in dimension order.
+__global__ void pq_encode_kernel(const float* des, long long n, const float* codebook, uint8_t* codes) {
+    __shared__ float cw[16 * 256 * 6 / 4];  // one quarter of the codebook per pass (24 KB)
+    const long long point = (long long)blockIdx.x * (blockDim.x / 16) + threadIdx.x / 16;
+    const int m = threadIdx.x & 15;
+    float d[6] = {0, 0, 0, 0, 0, 0};
+    if (point < n)
+        for (int k = 0; k < 6; ++k) d[k] = des[point * kDesLenD + m * 6 + k];
+    int best = 0;
+    for (int pass = 0; pass < 4; ++pass) {  // sub-quantizers 4*pass .. 4*pass+3
+        __syncthreads();
+        for (int e = threadIdx.x; e < 4 * 256 * 6; e += blockDim.x) cw[e] = codebook[pass * 4 * 256 * 6 + e];
+        __syncthreads();
+        if ((m >> 2) == pass && point < n) {
+            const float* w = cw + (m & 3) * 256 * 6;
+            float bd = CUDART_INF_F;
+            for (int c = 0; c < 256; ++c) {
+                float dist = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float t = f_sub(d[k], w[c * 6 + k]);
+                    dist = f_add(dist, f_mul(t, t));
+                }
+                if (dist < bd) {
+                    bd = dist;
+                    best = c;
+                }
+            }
+        }
+    }
+    if (point < n) codes[point * 16 + m] = (uint8_t)best;
+}
+
+// ---- gallery re-layout (ingest) --------------------------------------------------------------------
+// row-major descriptors [n][96] of template g -> k-major [96][np] (np = n rounded up to 4, zero
+// padded); coordinates -> short2.  grid = templates.
+struct RelayoutParams {
+    int n_templates;
+    const uint32_t* src_off;   // [n+1] unpadded offsets
+    const uint32_t* dst_off;   // [n+1] padded offsets
+    const int16_t* x;
+    const int16_t* y;
+    const float* ori;
+    const float* des;          // row-major
+    short2* out_xy;
+    float* out_ori;
+    float* out_desT;
+};
+
+__global__ void relayout_minutiae_kernel(RelayoutParams P) {
+    const int g = blockIdx.x;
+    const uint32_t s0 = P.src_off[g], n = P.src_off[g + 1] - s0;
+    const uint32_t d0 = P.dst_off[g], np = P.dst_off[g + 1] - d0;
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+        if (i < n) {
+            P.out_xy[d0 + i] = make_short2(P.x[s0 + i], P.y[s0 + i]);
+            P.out_ori[d0 + i] = P.ori[s0 + i];
+        } else {
+            P.out_xy[d0 + i] = make_short2(0, 0);
+            P.out_ori[d0 + i] = 0.0f;
+        }
+    }
+    float* dst = P.out_desT + (size_t)96 * d0;
+    const float* src = P.des + (size_t)96 * s0;
+    for (uint32_t e = threadIdx.x; e < 96 * np; e += blockDim.x) {
+        const uint32_t k = e / np, i = e - k * np;
+        dst[e] = (i < n) ? src[(size_t)i * 96 + k] : 0.0f;
+    }
+}
+
+__global__ void pack_xy_kernel(const int16_t* x, const int16_t* y, size_t n, short2* out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = make_short2(x[e], y[e]);
+}
+
+}  // namespace lafis

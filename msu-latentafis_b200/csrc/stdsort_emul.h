@@ -1,0 +1,163 @@
+// Reproduces the permutation libstdc++'s std::sort produces for the reference's index sorts.
+//
+// The reference ranks candidates with `std::sort(y.begin(), y.end(), [&](int a,int b){return
+// key[a] > key[b];})` (matching/matcher.cpp:476, :741, :1301, :1423, :1590).  std::sort is not
+// stable and LSS_R_Fast2 (:1556-1581) creates exact ties by construction, so WHICH of two tied
+// correspondences comes first decides which one survives the greedy selection.  The kernels sort in
+// parallel with the total order (key desc, index asc); whenever a tie can influence the result they
+// fall back to this routine, which walks through the introsort of GCC 13's bits/stl_algo.h
+// (median-of-3 to first, unguarded Hoare partition, recursion on the right part, depth limit
+// 2*floor(log2 n) with heap-sort fallback, final insertion sort with threshold 16) step for step.
+// For n <= 16 std::sort is a plain insertion sort, i.e. stable, and the total order is already
+// exact.  Host+device so that tests/test_stdsort.py can pin it against std::sort on the CPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LAFIS_SORT_HD __host__ __device__
+#else
+#define LAFIS_SORT_HD
+#endif
+
+namespace lafis {
+
+template <typename KeyT, typename IdxT>
+struct StdSortEmu {
+    const KeyT* key;
+    IdxT* y;
+
+    LAFIS_SORT_HD bool before(IdxT a, IdxT b) const { return key[a] > key[b]; }
+    LAFIS_SORT_HD void swp(int a, int b) {
+        IdxT t = y[a];
+        y[a] = y[b];
+        y[b] = t;
+    }
+    LAFIS_SORT_HD void unguarded_linear_insert(int last) {
+        IdxT val = y[last];
+        int next = last - 1;
+        while (before(val, y[next])) {
+            y[last] = y[next];
+            last = next;
+            --next;
+        }
+        y[last] = val;
+    }
+    LAFIS_SORT_HD void insertion_sort(int first, int last) {
+        if (first == last) return;
+        for (int i = first + 1; i != last; ++i) {
+            if (before(y[i], y[first])) {
+                IdxT val = y[i];
+                for (int k = i; k > first; --k) y[k] = y[k - 1];
+                y[first] = val;
+            } else {
+                unguarded_linear_insert(i);
+            }
+        }
+    }
+    LAFIS_SORT_HD void push_heap(int first, int hole, int top, IdxT value) {
+        int parent = (hole - 1) / 2;
+        while (hole > top && before(y[first + parent], value)) {
+            y[first + hole] = y[first + parent];
+            hole = parent;
+            parent = (hole - 1) / 2;
+        }
+        y[first + hole] = value;
+    }
+    LAFIS_SORT_HD void adjust_heap(int first, int hole, int len, IdxT value) {
+        const int top = hole;
+        int child = hole;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (before(y[first + child], y[first + child - 1])) child--;
+            y[first + hole] = y[first + child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            y[first + hole] = y[first + child - 1];
+            hole = child - 1;
+        }
+        push_heap(first, hole, top, value);
+    }
+    LAFIS_SORT_HD void heap_sort(int first, int last) {
+        const int len = last - first;
+        if (len >= 2) {
+            int parent = (len - 2) / 2;
+            for (;;) {
+                adjust_heap(first, parent, len, y[first + parent]);
+                if (parent == 0) break;
+                parent--;
+            }
+        }
+        while (last - first > 1) {
+            --last;
+            IdxT value = y[last];
+            y[last] = y[first];
+            adjust_heap(first, 0, last - first, value);
+        }
+    }
+    // one partition step on [first, last): returns the cut
+    LAFIS_SORT_HD int partition_pivot(int first, int last) {
+        const int mid = first + (last - first) / 2;
+        const int a = first + 1, b = mid, c = last - 1;
+        if (before(y[a], y[b])) {
+            if (before(y[b], y[c])) swp(first, b);
+            else if (before(y[a], y[c])) swp(first, c);
+            else swp(first, a);
+        } else if (before(y[a], y[c])) swp(first, a);
+        else if (before(y[b], y[c])) swp(first, c);
+        else swp(first, b);
+        int lo = first + 1, hi = last;
+        for (;;) {
+            while (before(y[lo], y[first])) ++lo;
+            --hi;
+            while (before(y[first], y[hi])) --hi;
+            if (!(lo < hi)) return lo;
+            swp(lo, hi);
+            ++lo;
+        }
+    }
+    // y must hold 0..n-1 on entry (std::iota)
+    LAFIS_SORT_HD void sort(int n) {
+        if (n <= 0) return;
+        int lg = 0;
+        for (int m = n; m > 1; m >>= 1) ++lg;
+        // __introsort_loop: recursion on [cut,last) happens BEFORE the loop continues on
+        // [first,cut); the partitions are disjoint, so an explicit stack of deferred left parts
+        // visits them with identical contents (order of processing does not change the result).
+        struct Frame {
+            int first, last, depth;
+        };
+        Frame stack[64];
+        int sp = 0;
+        stack[sp++] = Frame{0, n, 2 * lg};
+        while (sp > 0) {
+            Frame f = stack[--sp];
+            while (f.last - f.first > 16) {
+                if (f.depth == 0) {
+                    heap_sort(f.first, f.last);
+                    break;
+                }
+                --f.depth;
+                const int cut = partition_pivot(f.first, f.last);
+                if (sp < 64) stack[sp++] = Frame{f.first, cut, f.depth};  // the loop's continuation
+                f.first = cut;                                               // the recursive call
+            }
+        }
+        if (n > 16) {
+            insertion_sort(0, 16);
+            for (int i = 16; i != n; ++i) unguarded_linear_insert(i);
+        } else {
+            insertion_sort(0, n);
+        }
+    }
+};
+
+template <typename KeyT, typename IdxT>
+LAFIS_SORT_HD inline void std_sort_desc_emulate(const KeyT* key, IdxT* y, int n) {
+    for (int i = 0; i < n; ++i) y[i] = (IdxT)i;
+    StdSortEmu<KeyT, IdxT> s{key, y};
+    s.sort(n);
+}
+
+}  // namespace lafis
