@@ -153,6 +153,22 @@ LAFIS_API int lafis_match_device(lafis_ctx* ctx, lafis_latents* latents, int top
  * into global ones with the (score desc, index asc) rule; host memory. */
 LAFIS_API int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n_lists, int topk, lafis_hit* out);
 
+/* ---- drivers with the reference's score-file formats (SURVEY.md §8b "Score files") ----
+ *      lafis_one2list_matching  replaces PQ::Matcher::One2List_matching,  matcher.cpp:216-337:
+ *        writes <score_path><latent stem>.csv = "filename,score" + up to 24 rows
+ *        <rank>"<rolled path>",<score>; returns 0, -1 (no *.dat in rolled_dir), 1 (latent empty).
+ *      lafis_list2list_matching replaces PQ::Matcher::List2List_matching, matcher.cpp:96-214:
+ *        one CSV per latent with one row "<rolled path>",<score %.3f> per gallery file in
+ *        directory order, -1.000 for entries the reference leaves unscored.
+ *      score_path is a prefix (the reference concatenates strings: it needs a trailing '/').
+ *      The gallery parsed for a directory stays resident and is reused by later calls with the
+ *      same directory; lafis_forget_gallery_dir() drops that association. ---- */
+LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_template_file, const char* rolled_dir,
+                                      const char* score_path);
+LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
+                                       const char* score_path);
+LAFIS_API void lafis_forget_gallery_dir(lafis_ctx* ctx);
+
 /* ---- enrollment helper: PQ-encode descriptors with the context's codebook,
  *      TrainedPQEncoder.encode_multi, extraction/descriptor_PQ.py:19-27.  des/codes are device
  *      pointers when on_device != 0. ---- */

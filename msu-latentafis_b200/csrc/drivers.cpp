@@ -1,0 +1,198 @@
+// 1-vs-N and N-vs-N drivers with the reference's score-file formats, on top of the C ABI.
+//
+//   reference: PQ::Matcher::One2List_matching   matching/matcher.cpp:216-337
+//              PQ::Matcher::List2List_matching  matching/matcher.cpp:96-214
+//
+// Differences that are deliberate: the gallery is parsed ONCE into HBM instead of once per
+// (latent, rolled) pair (matcher.cpp:173, :278), and all latents of a directory are scored as
+// batches.  File names, CSV layouts, return codes and console messages follow the reference.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/latentafis_b200.h"
+#include "dat_format.h"
+
+namespace fs = std::filesystem;
+using namespace lafis;
+
+namespace {
+
+// the gallery already resident on `ctx` is reused when it was loaded from the same directory
+struct DirCache {
+    lafis_ctx* ctx = nullptr;
+    std::string dir;
+};
+DirCache g_cache;
+
+int ensure_gallery(lafis_ctx* ctx, const std::string& dir, bool announce) {
+    if (g_cache.ctx == ctx && g_cache.dir == dir && lafis_gallery_size(ctx) > 0) return LAFIS_OK;
+    std::vector<std::string> files = list_dat_files(dir);
+    if (announce)
+        for (const std::string& f : files) std::cout << "rolled template file" << fs::path(f) << std::endl;
+    if (files.empty()) {
+        std::cout << "No rolled templates found in directory: " << dir << std::endl;
+        return LAFIS_ERR_NO_TEMPLATES;
+    }
+    std::vector<const char*> ptrs(files.size());
+    for (size_t i = 0; i < files.size(); ++i) ptrs[i] = files[i].c_str();
+    int rc = lafis_gallery_load_files(ctx, ptrs.data(), (int)ptrs.size(), 0, 1);
+    if (rc == LAFIS_OK) {
+        g_cache.ctx = ctx;
+        g_cache.dir = dir;
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+LAFIS_API void lafis_forget_gallery_dir(lafis_ctx* ctx) {
+    if (g_cache.ctx == ctx) g_cache = DirCache();
+}
+
+LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_template_file, const char* rolled_dir,
+                                      const char* score_path) {
+    if (!ctx || !latent_template_file || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+    const fs::path latent_file(latent_template_file);
+    const std::string score_file = std::string(score_path) + latent_file.stem().string() + ".csv";
+    int rc = ensure_gallery(ctx, rolled_dir, false);
+    if (rc != LAFIS_OK) return rc;
+    const int G = lafis_gallery_size(ctx);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    std::cout << "Latent Query: " << latent_file << std::endl;
+    std::cout << "Gallery size: " << G << std::endl;
+
+    lafis_latents* L = nullptr;
+    const char* lp = latent_template_file;
+    rc = lafis_latents_load_files(ctx, &lp, 1, &L);
+    if (rc != LAFIS_OK) return rc;
+    const int st = lafis_latents_status(L, 0);
+    if (st == LAFIS_LATENT_EMPTY) {
+        // matcher.cpp:260-267 writes "0" when the latent holds no template at all; every pair then
+        // returns 1 and the driver exits with 1 (:296-299).  A latent with 1..26 minutiae templates
+        // and no texture template takes the same exit without the file.
+        LatentTemplate T;
+        read_latent_dat(latent_template_file, T);
+        if (T.n_minu_templates <= 0 && T.n_tex_templates <= 0) {
+            std::ofstream output(score_file);
+            output << 0 << std::endl;
+        }
+        std::cout << "Matching failed: latent template is empty. Exiting." << std::endl;
+        lafis_latents_free(L);
+        return LAFIS_LATENT_EMPTY;
+    }
+    if (st != LAFIS_OK) {
+        lafis_latents_free(L);
+        return st;
+    }
+    std::vector<float> scores((size_t)G, -1.0f);
+    rc = lafis_match(ctx, L, 0, nullptr, scores.data(), nullptr);
+    lafis_latents_free(L);
+    if (rc != LAFIS_OK) return rc;
+    for (int j = 0; j < G; ++j)
+        if (scores[j] == -1.0f && lafis_gallery_status(ctx, j) != LAFIS_TPL_OK &&
+            lafis_gallery_status(ctx, j) != LAFIS_TPL_TRUNCATED)
+            std::cout << "Comparison failed: rolled template is empty. Skipping." << std::endl;
+
+    // rank list: the reference's own call, std::sort with (scores[a] > scores[b]) (matcher.cpp:306-309)
+    std::vector<int> ind((size_t)G);
+    std::iota(ind.begin(), ind.end(), 0);
+    std::sort(ind.begin(), ind.end(), [&](const int& a, const int& b) { return scores[a] > scores[b]; });
+    std::ofstream output(score_file);
+    output << "filename,score" << std::endl;
+    std::cout << "Match Results" << std::endl;
+    std::cout << "----------------" << std::endl;
+    std::cout << "Rank     Filename      Score" << std::endl;
+    for (int j = 0; j < 24 && j < G; ++j) {
+        const fs::path rolled(lafis_gallery_path(ctx, ind[j]));
+        output << std::to_string(j + 1) << rolled << "," << scores[ind[j]] << std::endl;
+        std::cout << std::to_string(j + 1) << "        " << rolled.filename() << "       " << scores[ind[j]] << std::endl;
+    }
+    output.close();
+    const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
+    std::cout << "Total matching duration (ms): " << span.count() << std::endl;
+    return LAFIS_OK;
+}
+
+LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
+                                       const char* score_path) {
+    if (!ctx || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+    std::vector<std::string> latent_files = list_dat_files(latent_dir);
+    for (const std::string& f : latent_files) std::cout << "latent template file" << fs::path(f) << std::endl;
+    if (latent_files.empty()) {
+        std::cout << "No latent templates found in directory: " << latent_dir << std::endl;
+        return LAFIS_ERR_NO_TEMPLATES;
+    }
+    int rc = ensure_gallery(ctx, rolled_dir, true);
+    if (rc != LAFIS_OK) return rc;
+    const int G = lafis_gallery_size(ctx);
+    std::cout << "Gallery size: " << G << std::endl;
+    const auto t0 = std::chrono::high_resolution_clock::now();
+
+    const int n = (int)latent_files.size();
+    // batches bounded by the size of the host score matrix (256 MB)
+    const int batch = std::max(1, std::min(n, (int)(((size_t)64 << 20) / (size_t)std::max(G, 1))));
+    std::vector<float> scores;
+    for (int b0 = 0; b0 < n; b0 += batch) {
+        const int nb = std::min(batch, n - b0);
+        std::vector<const char*> ptrs(nb);
+        for (int i = 0; i < nb; ++i) ptrs[i] = latent_files[b0 + i].c_str();
+        lafis_latents* L = nullptr;
+        rc = lafis_latents_load_files(ctx, ptrs.data(), nb, &L);
+        if (rc != LAFIS_OK) return rc;
+        scores.assign((size_t)nb * G, -1.0f);
+        bool any = false;
+        for (int i = 0; i < nb; ++i) any = any || lafis_latents_status(L, i) == LAFIS_OK;
+        if (any) {
+            rc = lafis_match(ctx, L, 0, nullptr, scores.data(), nullptr);
+            if (rc != LAFIS_OK) {
+                lafis_latents_free(L);
+                return rc;
+            }
+        }
+        for (int i = 0; i < nb; ++i) {
+            const fs::path lf(latent_files[b0 + i]);
+            std::cout << lf << std::endl;
+            const std::string out_name = std::string(score_path) + lf.stem().string() + ".csv";
+            const int st = lafis_latents_status(L, i);
+            if (st == LAFIS_LATENT_EMPTY) {
+                LatentTemplate T;
+                read_latent_dat(latent_files[b0 + i], T);
+                std::cout << "Latent minutiae templates: " << T.n_minu_templates << std::endl;
+                std::cout << "Latent texture templates: " << T.n_tex_templates << std::endl;
+                if (T.n_minu_templates <= 0 && T.n_tex_templates <= 0) {  // matcher.cpp:153-163
+                    std::cout << "No minutiae or texture templates found" << std::endl;
+                    std::ofstream output(out_name);
+                    output << 0 << std::endl;
+                } else {  // matcher.cpp:191-194
+                    std::cout << "Matching failed: latent template is empty. Skipping." << std::endl;
+                }
+                continue;
+            }
+            if (st != LAFIS_OK) {
+                std::cout << "Matching failed: latent template layout is outside the matcher's domain. Skipping."
+                          << std::endl;
+                continue;
+            }
+            std::ofstream output(out_name);
+            for (int j = 0; j < G; ++j)
+                output << fs::path(lafis_gallery_path(ctx, j)) << "," << std::setprecision(3) << std::fixed
+                       << scores[(size_t)i * G + j] << std::endl;
+        }
+        lafis_latents_free(L);
+    }
+    const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
+    std::cout << "Total matching duration (ms): " << span.count() << std::endl;
+    return LAFIS_OK;
+}
+
+}  // extern "C"

@@ -270,7 +270,7 @@ constexpr int kGraphMinuThreads = 128;
 constexpr size_t kGraphMinuSmem = sizeof(float) * kTopCorrMinu * kTopCorrMinu + sizeof(GraphWork<kTopCorrMinu>);
 
 __global__ void __launch_bounds__(kGraphMinuThreads) graph_minu_kernel(GraphMinuParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     float* H = reinterpret_cast<float*>(smem);
     GraphWork<kTopCorrMinu>& w = *reinterpret_cast<GraphWork<kTopCorrMinu>*>(smem + sizeof(float) * kTopCorrMinu * kTopCorrMinu);
     const int tid = threadIdx.x;
@@ -333,7 +333,7 @@ constexpr size_t kGraphTexSmem =
     sizeof(float) * kTopCorrTex * kTopCorrTex + sizeof(GraphWork<kTopCorrTex>) + sizeof(TexRowWork);
 
 __global__ void __launch_bounds__(kGraphTexThreads) graph_tex_kernel(GraphTexParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     float* H = reinterpret_cast<float*>(smem);
     GraphWork<kTopCorrTex>& w = *reinterpret_cast<GraphWork<kTopCorrTex>*>(smem + sizeof(float) * kTopCorrTex * kTopCorrTex);
     TexRowWork& r = *reinterpret_cast<TexRowWork*>(smem + sizeof(float) * kTopCorrTex * kTopCorrTex + sizeof(GraphWork<kTopCorrTex>));
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kGraphTexThreads) graph_tex_kernel(GraphTexPar
         __syncthreads();
         if (r.flag) {
             if (tid == 0) {
-                std_sort_desc_emulate<float, int>(r.rv, r.ry, nLt);
+                std_sort_desc_prefix(DenseKey<float>{r.rv}, r.ry, nLt, kTopCorrTex);
                 atomicAdd(P.slow_path_count, 1ull);
             }
             __syncthreads();

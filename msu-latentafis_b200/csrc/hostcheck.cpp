@@ -1,0 +1,77 @@
+// Host build of the bit-exact helper headers and the .dat parsers for the CPU unit tests
+// (tests/test_host_math.py, tests/test_dat_format.py).  Not part of the GPU library.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "dat_format.h"
+#include "exact_math.h"
+#include "stdsort_emul.h"
+
+using namespace lafis;
+
+extern "C" {
+
+float hc_atan2f(float y, float x) { return atan2f_fdlibm(y, x); }
+void hc_atan2f_many(const float* y, const float* x, float* out, long n) {
+    for (long i = 0; i < n; ++i) out[i] = atan2f_fdlibm(y[i], x[i]);
+}
+
+// first `need` positions of the emulated std::sort permutation
+void hc_sort_prefix(const float* key, int n, int need, int* out) {
+    std::vector<int> y((size_t)std::max(n, 1));
+    std_sort_desc_prefix(DenseKey<float>{key}, y.data(), n, need);
+    std::copy(y.begin(), y.begin() + std::min(n, need), out);
+}
+void hc_sort_prefix_u16(const float* key, int n, int need, int* out) {
+    std::vector<uint16_t> y((size_t)std::max(n, 1));
+    std_sort_desc_prefix(DenseKey<float>{key}, y.data(), n, need);
+    for (int i = 0; i < std::min(n, need); ++i) out[i] = y[i];
+}
+// libstdc++'s own answer, with the reference's comparator shape (matcher.cpp:475-476)
+void hc_std_sort(const float* key, int n, int* out) {
+    std::vector<int> y((size_t)n);
+    std::iota(y.begin(), y.end(), 0);
+    std::sort(y.begin(), y.end(), [key](int a, int b) { return key[a] > key[b]; });
+    std::copy(y.begin(), y.end(), out);
+}
+
+// parsers: counts and a checksum of what was kept
+int hc_read_rolled(const char* path, int* status, int* n_minu_t, int* n_tex_t, int* n_minu, int* n_tex) {
+    RolledTemplate R;
+    int rc = read_rolled_dat(path, R);
+    *status = R.status;
+    *n_minu_t = R.n_minu_templates;
+    *n_tex_t = R.n_tex_templates;
+    *n_minu = R.minu.n();
+    *n_tex = R.tex.n();
+    return rc;
+}
+int hc_read_latent(const char* path, int* n_minu_t, int* n_tex_t, int* slot_n, int* n_tex) {
+    LatentTemplate T;
+    int rc = read_latent_dat(path, T);
+    *n_minu_t = T.n_minu_templates;
+    *n_tex_t = T.n_tex_templates;
+    for (int s = 0; s < 3; ++s) slot_n[s] = T.minu[s].n();
+    *n_tex = T.tex.n();
+    return rc;
+}
+int hc_rolled_arrays(const char* path, short* mx, short* my, float* mori, float* mdes, short* tx, short* ty, float* tori,
+                     unsigned char* codes) {
+    RolledTemplate R;
+    int rc = read_rolled_dat(path, R);
+    auto cp = [](void* d, const void* s, size_t b) {
+        if (d && b) std::memcpy(d, s, b);
+    };
+    cp(mx, R.minu.x.data(), 2 * R.minu.x.size());
+    cp(my, R.minu.y.data(), 2 * R.minu.y.size());
+    cp(mori, R.minu.ori.data(), 4 * R.minu.ori.size());
+    cp(mdes, R.minu.des.data(), 4 * R.minu.des.size());
+    cp(tx, R.tex.x.data(), 2 * R.tex.x.size());
+    cp(ty, R.tex.y.data(), 2 * R.tex.y.size());
+    cp(tori, R.tex.ori.data(), 4 * R.tex.ori.size());
+    cp(codes, R.tex.codes.data(), R.tex.codes.size());
+    return rc;
+}
+}

@@ -1,0 +1,1052 @@
+// C-ABI implementation (include/latentafis_b200.h): context, gallery ingest into HBM, latent
+// staging, the chunked match pipeline and rank lists.  Host-side counterpart of PQ::Matcher
+// (matching/matcher.h:34-75, matching/matcher.cpp:31-337); all arithmetic of the hot path happens in
+// the kernels included below.  There is no CPU implementation of any scoring stage in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/latentafis_b200.h"
+#include "dat_format.h"
+#include "device_common.cuh"
+#include "graph_prune.cuh"
+#include "minu_corr.cuh"
+#include "misc_kernels.cuh"
+#include "tex_rowmax.cuh"
+
+using namespace lafis;
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = std::max<size_t>(n, 1);
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct lafis_latents {
+    int n = 0;
+    std::vector<int> status;            // LAFIS_OK / LAFIS_LATENT_EMPTY / LAFIS_ERR_LATENT_LAYOUT
+    std::vector<int> tex_weighted;
+    // host staging, already in device layout
+    int lt_stride = 8;
+    int max_slot_n = 0;
+    std::vector<int> slot_n;            // [3n]
+    std::vector<uint32_t> slot_off;     // [3n] padded offsets
+    uint32_t tot_minu_padded = 0;
+    std::vector<short2> minu_xy;
+    std::vector<float> minu_ori;
+    std::vector<float> minu_desT;
+    std::vector<int> tex_n;             // [n]
+    std::vector<short2> tex_xy;         // [n][lt_stride]
+    std::vector<float> tex_ori;
+    std::vector<float> tex_des;         // [n][lt_stride][96]
+    // one pinned arena holding everything above back to back (single H2D copy)
+    unsigned char* pinned = nullptr;
+    size_t arena_bytes = 0;
+    size_t o_slot_n = 0, o_slot_off = 0, o_minu_xy = 0, o_minu_ori = 0, o_minu_desT = 0, o_tex_n = 0, o_tex_xy = 0,
+           o_tex_ori = 0, o_tex_des = 0, o_weighted = 0, o_status = 0;
+    // device residency
+    lafis_ctx* owner = nullptr;
+    unsigned char* d_arena = nullptr;
+    bool resident = false;
+};
+
+struct lafis_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[8] = {};
+    std::string err;
+    int sm_count = 148;
+    size_t work_budget = (size_t)8 << 30;
+    bool profile = false;
+
+    float* d_codebook = nullptr;  // [16][256][6]
+    float* d_table = nullptr;     // [50*50]
+
+    // gallery
+    DeviceGallery gal;
+    uint32_t index_base = 0;
+    std::vector<std::string> paths;
+    std::vector<int8_t> h_status;
+    std::vector<uint32_t> h_minu_off;  // padded
+    std::vector<uint16_t> h_minu_n;
+    std::vector<uint32_t> h_tex_off;
+    int max_nR = 0, max_nRt = 0;
+    uint64_t algo_bytes = 0;
+
+    // work buffers
+    DevBuf<float> rowmax_val;
+    DevBuf<uint16_t> rowmax_j;
+    DevBuf<float> corr_v;
+    DevBuf<uint32_t> corr_ij;
+    DevBuf<int> corr_n;
+    DevBuf<float> comp;
+    DevBuf<float> final_scores;
+    DevBuf<unsigned long long> keys_a, keys_b;
+    DevBuf<HitDev> hits;
+    DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
+    int* d_job_counter = nullptr;
+    unsigned long long* d_slow = nullptr;  // [2] introsort replays: minutiae top-120, texture top-200
+
+    lafis_stats stats{};
+};
+
+namespace {
+
+std::string g_create_error;  // failures before a context exists (lafis_last_error(NULL))
+
+int fail(lafis_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define LAFIS_CUDA(c, expr)                                                                            \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail((c), LAFIS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                           \
+    } while (0)
+
+void free_gallery(lafis_ctx* c) {
+    DeviceGallery& g = c->gal;
+    cudaFree(g.minu_off);
+    cudaFree(g.minu_n);
+    cudaFree(g.minu_xy);
+    cudaFree(g.minu_ori);
+    cudaFree(g.minu_desT);
+    cudaFree(g.tex_off);
+    cudaFree(g.tex_xy);
+    cudaFree(g.tex_ori);
+    cudaFree(g.tex_codes);
+    cudaFree(g.status);
+    g = DeviceGallery();
+    c->paths.clear();
+    c->h_status.clear();
+    c->h_minu_off.clear();
+    c->h_minu_n.clear();
+    c->h_tex_off.clear();
+    c->max_nR = c->max_nRt = 0;
+    c->algo_bytes = 0;
+}
+
+int create_common(const float* codewords, int device, lafis_ctx** out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        return fail(nullptr, LAFIS_ERR_CUDA, "no CUDA device %d (%s)", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, LAFIS_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)  // built for sm_100a only; no other code path exists
+        return fail(nullptr, LAFIS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    lafis_ctx* c = new lafis_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (const char* s = getenv("LAFIS_WORK_BYTES")) c->work_budget = (size_t)strtoull(s, nullptr, 10);
+    if (const char* s = getenv("LAFIS_PROFILE")) c->profile = atoi(s) != 0;
+    cudaError_t last = cudaSuccess;
+    const char* what = "";
+#define TRY(expr) (ok = ok && ((last = (expr)) == cudaSuccess || (what = #expr, false)))
+    bool ok = true;
+    TRY(cudaSetDevice(device));
+    ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->evs[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_slow, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) {
+        // matcher.cpp:49-56: table[i*50+j] = (float)sqrt((16 i)^2 + (16 j)^2), square root in double
+        std::vector<float> table(kTableN * kTableN);
+        for (int i = 0; i < kTableN; ++i)
+            for (int j = 0; j < kTableN; ++j)
+                table[i * kTableN + j] = (float)std::sqrt((i * 16.0) * (i * 16.0) + (j * 16.0) * (j * 16.0));
+        ok = cudaMemcpy(c->d_table, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(c->d_codebook, codewords, sizeof(float) * kSubs * kClusters * kSubDim,
+                              cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemset(c->d_slow, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
+        TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
+        TRY(cudaFuncSetAttribute(minu_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrMaxDynSmem));
+        TRY(cudaFuncSetAttribute(graph_minu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphMinuSmem));
+        TRY(cudaFuncSetAttribute(graph_tex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphTexSmem));
+    }
+#undef TRY
+    if (!ok) {
+        if (last == cudaSuccess) last = cudaGetLastError();
+        fail(nullptr, LAFIS_ERR_CUDA, "context setup failed: %s %s", what, cudaGetErrorString(last));
+        lafis_destroy(c);
+        return LAFIS_ERR_CUDA;
+    }
+    *out = c;
+    return LAFIS_OK;
+}
+
+// Everything a packed gallery needs on the host before the device re-layout.
+struct IngestPlan {
+    std::vector<uint32_t> dst_minu_off, dst_tex_off;
+    std::vector<uint16_t> minu_n;
+    std::vector<int8_t> status;
+    bool tex_truncated = false;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* lafis_version(void) { return "latentafis_b200 0.1 (sm_100a)"; }
+
+int lafis_create_from_codebook(const float* codewords, int subs, int clusters, int sub_dim, int device,
+                               lafis_ctx** out) {
+    if (!codewords || !out) return LAFIS_ERR_ARG;
+    if (subs != kSubs || clusters != kClusters || sub_dim != kSubDim) return LAFIS_ERR_CODEBOOK;
+    return create_common(codewords, device, out);
+}
+
+int lafis_create(const char* codebook_path, int device, lafis_ctx** out) {
+    if (!codebook_path || !out) return LAFIS_ERR_ARG;
+    std::vector<float> cw;
+    int subs = 0, clusters = 0, sub_dim = 0;
+    int rc = read_codebook(codebook_path, cw, subs, clusters, sub_dim);
+    if (rc == -3) return LAFIS_ERR_IO;
+    if (rc != 0) return LAFIS_ERR_CODEBOOK;
+    return lafis_create_from_codebook(cw.data(), subs, clusters, sub_dim, device, out);
+}
+
+void lafis_destroy(lafis_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_gallery(c);
+    c->rowmax_val.release();
+    c->rowmax_j.release();
+    c->corr_v.release();
+    c->corr_ij.release();
+    c->corr_n.release();
+    c->comp.release();
+    c->final_scores.release();
+    c->keys_a.release();
+    c->keys_b.release();
+    c->hits.release();
+    c->lat_arena.release();
+    cudaFree(c->d_codebook);
+    cudaFree(c->d_table);
+    cudaFree(c->d_job_counter);
+    cudaFree(c->d_slow);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 8; ++i)
+        if (c->evs[i]) cudaEventDestroy(c->evs[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* lafis_last_error(const lafis_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+void* lafis_stream(const lafis_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int lafis_get_stats(const lafis_ctx* c, lafis_stats* out) {
+    if (!c || !out) return LAFIS_ERR_ARG;
+    *out = c->stats;
+    return LAFIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gallery ingest
+// ---------------------------------------------------------------------------------------------------
+int lafis_gallery_set_packed(lafis_ctx* c, const lafis_packed_gallery* g, uint32_t index_base) {
+    if (!c || !g || g->n_templates < 0 || !g->minu_off || !g->tex_off) return fail(c, LAFIS_ERR_ARG, "bad gallery argument");
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_gallery(c);
+    const int n = g->n_templates;
+    c->index_base = index_base;
+    if (n == 0) return LAFIS_OK;
+
+    // ---- host plan ----
+    std::vector<uint32_t> dst_minu_off(n + 1), dst_tex_off(n + 1);
+    std::vector<uint16_t> minu_n(n);
+    std::vector<int8_t> status(n);
+    bool tex_truncated = false;
+    int max_nR = 0, max_nRt = 0;
+    uint64_t algo = 0;
+    dst_minu_off[0] = dst_tex_off[0] = 0;
+    for (int t = 0; t < n; ++t) {
+        const uint32_t nm = g->minu_off[t + 1] - g->minu_off[t];
+        uint32_t nt = g->tex_off[t + 1] - g->tex_off[t];
+        if (nm > (uint32_t)kMaxMinutiae) return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE, "template %d: %u minutiae", t, nm);
+        if (nt > (uint32_t)kMaxTexture) {  // matcher.cpp:546-547
+            nt = kMaxTexture;
+            tex_truncated = true;
+        }
+        minu_n[t] = (uint16_t)nm;
+        dst_minu_off[t + 1] = dst_minu_off[t] + ((nm + 3u) & ~3u);
+        dst_tex_off[t + 1] = dst_tex_off[t] + nt;
+        max_nR = std::max(max_nR, (int)nm);
+        max_nRt = std::max(max_nRt, (int)nt);
+        int8_t st = g->status ? g->status[t] : (int8_t)LAFIS_TPL_OK;
+        if ((st == LAFIS_TPL_OK || st == LAFIS_TPL_TRUNCATED) && nm == 0 && nt == 0) st = LAFIS_TPL_EMPTY;
+        status[t] = st;
+        algo += 392ull * nm + 24ull * nt;
+    }
+    const uint32_t src_minu_tot = g->minu_off[n], src_tex_tot = g->tex_off[n];
+    const uint32_t dst_minu_tot = dst_minu_off[n], dst_tex_tot = dst_tex_off[n];
+
+    // ---- source arrays on the device ----
+    const int16_t *sx = g->minu_x, *sy = g->minu_y, *tx = g->tex_x, *ty = g->tex_y;
+    const float *sori = g->minu_ori, *sdes = g->minu_des, *tori = g->tex_ori;
+    const uint8_t* tcodes = g->tex_codes;
+    std::vector<void*> temps;
+    auto cleanup = [&]() {
+        for (void* p : temps) cudaFree(p);
+        temps.clear();
+    };
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        temps.push_back(d);
+        if (bytes) e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c->stream);
+        *dst = d;
+        return e;
+    };
+#define LAFIS_CUDA_T(expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            cleanup();                                                                                  \
+            free_gallery(c);                                                                            \
+            return fail(c, LAFIS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                        __FILE__, __LINE__);                                                            \
+        }                                                                                               \
+    } while (0)
+
+    // texture truncation (> 1000 points) needs a per-template gather; do it on the host side of the
+    // offsets only: the copy kernels below take src and dst offsets separately.
+    if (!g->on_device) {
+        LAFIS_CUDA_T(up(g->minu_x, 2ull * src_minu_tot, (const void**)&sx));
+        LAFIS_CUDA_T(up(g->minu_y, 2ull * src_minu_tot, (const void**)&sy));
+        LAFIS_CUDA_T(up(g->minu_ori, 4ull * src_minu_tot, (const void**)&sori));
+        LAFIS_CUDA_T(up(g->minu_des, 4ull * kDesLen * src_minu_tot, (const void**)&sdes));
+        LAFIS_CUDA_T(up(g->tex_x, 2ull * src_tex_tot, (const void**)&tx));
+        LAFIS_CUDA_T(up(g->tex_y, 2ull * src_tex_tot, (const void**)&ty));
+        LAFIS_CUDA_T(up(g->tex_ori, 4ull * src_tex_tot, (const void**)&tori));
+        LAFIS_CUDA_T(up(g->tex_codes, 16ull * src_tex_tot, (const void**)&tcodes));
+    }
+    const uint32_t *d_src_minu_off = nullptr, *d_src_tex_off = nullptr;
+    LAFIS_CUDA_T(up(g->minu_off, 4ull * (n + 1), (const void**)&d_src_minu_off));
+    LAFIS_CUDA_T(up(g->tex_off, 4ull * (n + 1), (const void**)&d_src_tex_off));
+
+    // ---- resident arrays ----
+    DeviceGallery& G = c->gal;
+    G.n = n;
+    LAFIS_CUDA_T(cudaMalloc(&G.minu_off, 4ull * (n + 1)));
+    LAFIS_CUDA_T(cudaMalloc(&G.minu_n, 2ull * n));
+    LAFIS_CUDA_T(cudaMalloc(&G.minu_xy, sizeof(short2) * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_T(cudaMalloc(&G.minu_ori, 4ull * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_T(cudaMalloc(&G.minu_desT, 4ull * kDesLen * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_T(cudaMalloc(&G.tex_off, 4ull * (n + 1)));
+    LAFIS_CUDA_T(cudaMalloc(&G.tex_xy, sizeof(short2) * std::max<size_t>(dst_tex_tot, 4)));
+    LAFIS_CUDA_T(cudaMalloc(&G.tex_ori, 4ull * std::max<size_t>(dst_tex_tot, 4)));
+    LAFIS_CUDA_T(cudaMalloc(&G.tex_codes, 16ull * ((size_t)dst_tex_tot + 32)));
+    LAFIS_CUDA_T(cudaMalloc(&G.status, (size_t)n));
+    LAFIS_CUDA_T(cudaMemcpyAsync(G.minu_off, dst_minu_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_T(cudaMemcpyAsync(G.minu_n, minu_n.data(), 2ull * n, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_T(cudaMemcpyAsync(G.tex_off, dst_tex_off.data(), 4ull * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_T(cudaMemcpyAsync(G.status, status.data(), (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_T(cudaMemsetAsync(G.tex_codes + dst_tex_tot, 0, 16ull * 32, c->stream));
+
+    RelayoutParams rp;
+    rp.n_templates = n;
+    rp.src_off = d_src_minu_off;
+    rp.dst_off = G.minu_off;
+    rp.x = sx;
+    rp.y = sy;
+    rp.ori = sori;
+    rp.des = sdes;
+    rp.out_xy = G.minu_xy;
+    rp.out_ori = G.minu_ori;
+    rp.out_desT = G.minu_desT;
+    relayout_minutiae_kernel<<<n, 256, 0, c->stream>>>(rp);
+    TexCopyParams tp;
+    tp.src_off = d_src_tex_off;
+    tp.dst_off = G.tex_off;
+    tp.x = tx;
+    tp.y = ty;
+    tp.ori = tori;
+    tp.codes = reinterpret_cast<const uint4*>(tcodes);
+    tp.codes_aligned = ((uintptr_t)tcodes & 15u) == 0;
+    tp.out_xy = G.tex_xy;
+    tp.out_ori = G.tex_ori;
+    tp.out_codes = G.tex_codes;
+    copy_texture_kernel<<<n, 256, 0, c->stream>>>(tp);
+    c->stats.kernel_launches += 2;
+    LAFIS_CUDA_T(cudaGetLastError());
+    LAFIS_CUDA_T(cudaStreamSynchronize(c->stream));
+    cleanup();
+#undef LAFIS_CUDA_T
+    (void)tex_truncated;
+
+    c->h_status.swap(status);
+    c->h_minu_off.swap(dst_minu_off);
+    c->h_minu_n.swap(minu_n);
+    c->h_tex_off.swap(dst_tex_off);
+    c->max_nR = max_nR;
+    c->max_nRt = max_nRt;
+    c->algo_bytes = algo;
+    c->paths.assign(n, std::string());
+    return LAFIS_OK;
+}
+
+int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int shard_rank, int shard_count) {
+    if (!c || (!paths && n > 0) || n < 0 || shard_count <= 0 || shard_rank < 0 || shard_rank >= shard_count)
+        return fail(c, LAFIS_ERR_ARG, "bad argument");
+    if (n == 0) return fail(c, LAFIS_ERR_NO_TEMPLATES, "no rolled templates");
+    const long long lo = (long long)n * shard_rank / shard_count, hi = (long long)n * (shard_rank + 1) / shard_count;
+    const int m = (int)(hi - lo);
+    std::vector<uint32_t> minu_off(m + 1, 0), tex_off(m + 1, 0);
+    std::vector<int16_t> mx, my, tx, ty;
+    std::vector<float> mori, mdes, tori;
+    std::vector<uint8_t> codes;
+    std::vector<int8_t> status(m);
+    std::vector<std::string> kept(m);
+    for (int t = 0; t < m; ++t) {
+        RolledTemplate R;
+        read_rolled_dat(paths[lo + t], R);
+        kept[t] = paths[lo + t];
+        status[t] = (int8_t)R.status;
+        mx.insert(mx.end(), R.minu.x.begin(), R.minu.x.end());
+        my.insert(my.end(), R.minu.y.begin(), R.minu.y.end());
+        mori.insert(mori.end(), R.minu.ori.begin(), R.minu.ori.end());
+        mdes.insert(mdes.end(), R.minu.des.begin(), R.minu.des.end());
+        tx.insert(tx.end(), R.tex.x.begin(), R.tex.x.end());
+        ty.insert(ty.end(), R.tex.y.begin(), R.tex.y.end());
+        tori.insert(tori.end(), R.tex.ori.begin(), R.tex.ori.end());
+        codes.insert(codes.end(), R.tex.codes.begin(), R.tex.codes.end());
+        minu_off[t + 1] = (uint32_t)mx.size();
+        tex_off[t + 1] = (uint32_t)tx.size();
+    }
+    lafis_packed_gallery g{};
+    g.n_templates = m;
+    g.minu_off = minu_off.data();
+    g.minu_x = mx.data();
+    g.minu_y = my.data();
+    g.minu_ori = mori.data();
+    g.minu_des = mdes.data();
+    g.tex_off = tex_off.data();
+    g.tex_x = tx.data();
+    g.tex_y = ty.data();
+    g.tex_ori = tori.data();
+    g.tex_codes = codes.data();
+    g.status = status.data();
+    g.on_device = 0;
+    int rc = lafis_gallery_set_packed(c, &g, (uint32_t)lo);
+    if (rc == LAFIS_OK) c->paths.swap(kept);
+    return rc;
+}
+
+int lafis_gallery_load_dir(lafis_ctx* c, const char* dir, int shard_rank, int shard_count) {
+    if (!c || !dir) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    std::vector<std::string> files = list_dat_files(dir);
+    if (files.empty()) return fail(c, LAFIS_ERR_NO_TEMPLATES, "No rolled templates found in directory: %s", dir);
+    std::vector<const char*> ptrs(files.size());
+    for (size_t i = 0; i < files.size(); ++i) ptrs[i] = files[i].c_str();
+    return lafis_gallery_load_files(c, ptrs.data(), (int)ptrs.size(), shard_rank, shard_count);
+}
+
+int lafis_gallery_size(const lafis_ctx* c) { return c ? c->gal.n : 0; }
+const char* lafis_gallery_path(const lafis_ctx* c, int i) {
+    return (c && i >= 0 && i < (int)c->paths.size()) ? c->paths[i].c_str() : "";
+}
+int lafis_gallery_status(const lafis_ctx* c, int i) {
+    return (c && i >= 0 && i < (int)c->h_status.size()) ? c->h_status[i] : LAFIS_TPL_FAILED;
+}
+uint64_t lafis_gallery_bytes(const lafis_ctx* c) { return c ? c->algo_bytes : 0; }
+
+int lafis_gallery_get_template(const lafis_ctx* cc, int t, int* n_minu, int16_t* mx, int16_t* my, float* mori,
+                               float* mdes, int* n_tex, int16_t* tx, int16_t* ty, float* tori, uint8_t* tcodes) {
+    lafis_ctx* c = const_cast<lafis_ctx*>(cc);
+    if (!c || t < 0 || t >= c->gal.n) return fail(c, LAFIS_ERR_ARG, "template index out of range");
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    const int nm = c->h_minu_n[t];
+    const int np = (int)(c->h_minu_off[t + 1] - c->h_minu_off[t]);
+    const uint32_t mo = c->h_minu_off[t], to = c->h_tex_off[t];
+    const int nt = (int)(c->h_tex_off[t + 1] - to);
+    if (n_minu) *n_minu = nm;
+    if (n_tex) *n_tex = nt;
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nm > 0 && (mx || my)) {
+        std::vector<short2> xy(nm);
+        LAFIS_CUDA(c, cudaMemcpy(xy.data(), c->gal.minu_xy + mo, sizeof(short2) * nm, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nm; ++i) {
+            if (mx) mx[i] = xy[i].x;
+            if (my) my[i] = xy[i].y;
+        }
+    }
+    if (nm > 0 && mori) LAFIS_CUDA(c, cudaMemcpy(mori, c->gal.minu_ori + mo, 4ull * nm, cudaMemcpyDeviceToHost));
+    if (nm > 0 && mdes) {
+        std::vector<float> T((size_t)kDesLen * np);
+        LAFIS_CUDA(c, cudaMemcpy(T.data(), c->gal.minu_desT + (size_t)kDesLen * mo, 4ull * kDesLen * np,
+                                 cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nm; ++i)
+            for (int k = 0; k < kDesLen; ++k) mdes[(size_t)i * kDesLen + k] = T[(size_t)k * np + i];
+    }
+    if (nt > 0 && (tx || ty)) {
+        std::vector<short2> xy(nt);
+        LAFIS_CUDA(c, cudaMemcpy(xy.data(), c->gal.tex_xy + to, sizeof(short2) * nt, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nt; ++i) {
+            if (tx) tx[i] = xy[i].x;
+            if (ty) ty[i] = xy[i].y;
+        }
+    }
+    if (nt > 0 && tori) LAFIS_CUDA(c, cudaMemcpy(tori, c->gal.tex_ori + to, 4ull * nt, cudaMemcpyDeviceToHost));
+    if (nt > 0 && tcodes) LAFIS_CUDA(c, cudaMemcpy(tcodes, c->gal.tex_codes + to, 16ull * nt, cudaMemcpyDeviceToHost));
+    return LAFIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// latents
+// ---------------------------------------------------------------------------------------------------
+static int finish_latents(lafis_ctx* c, lafis_latents* L) {
+    // lay the staging vectors out in one pinned arena
+    const int n = L->n;
+    auto place = [](size_t& cur, size_t bytes) {
+        size_t at = cur;
+        cur = (cur + bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    size_t cur = 0;
+    L->o_slot_n = place(cur, sizeof(int) * 3 * n);
+    L->o_slot_off = place(cur, sizeof(uint32_t) * 3 * n);
+    L->o_minu_xy = place(cur, sizeof(short2) * L->minu_xy.size());
+    L->o_minu_ori = place(cur, sizeof(float) * L->minu_ori.size());
+    L->o_minu_desT = place(cur, sizeof(float) * L->minu_desT.size());
+    L->o_tex_n = place(cur, sizeof(int) * n);
+    L->o_tex_xy = place(cur, sizeof(short2) * L->tex_xy.size());
+    L->o_tex_ori = place(cur, sizeof(float) * L->tex_ori.size());
+    L->o_tex_des = place(cur, sizeof(float) * L->tex_des.size());
+    L->o_weighted = place(cur, sizeof(int) * n);
+    L->o_status = place(cur, sizeof(int) * n);
+    L->arena_bytes = cur;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMallocHost(&L->pinned, std::max<size_t>(cur, 256)) != cudaSuccess)
+        return fail(c, LAFIS_ERR_CUDA, "cudaMallocHost(%zu) failed", cur);
+    auto put = [&](size_t off, const void* src, size_t bytes) {
+        if (bytes) std::memcpy(L->pinned + off, src, bytes);
+    };
+    put(L->o_slot_n, L->slot_n.data(), sizeof(int) * L->slot_n.size());
+    put(L->o_slot_off, L->slot_off.data(), sizeof(uint32_t) * L->slot_off.size());
+    put(L->o_minu_xy, L->minu_xy.data(), sizeof(short2) * L->minu_xy.size());
+    put(L->o_minu_ori, L->minu_ori.data(), sizeof(float) * L->minu_ori.size());
+    put(L->o_minu_desT, L->minu_desT.data(), sizeof(float) * L->minu_desT.size());
+    put(L->o_tex_n, L->tex_n.data(), sizeof(int) * L->tex_n.size());
+    put(L->o_tex_xy, L->tex_xy.data(), sizeof(short2) * L->tex_xy.size());
+    put(L->o_tex_ori, L->tex_ori.data(), sizeof(float) * L->tex_ori.size());
+    put(L->o_tex_des, L->tex_des.data(), sizeof(float) * L->tex_des.size());
+    put(L->o_weighted, L->tex_weighted.data(), sizeof(int) * L->tex_weighted.size());
+    put(L->o_status, L->status.data(), sizeof(int) * L->status.size());
+    // the vectors are no longer needed once the arena is filled
+    std::vector<short2>().swap(L->minu_xy);
+    std::vector<float>().swap(L->minu_ori);
+    std::vector<float>().swap(L->minu_desT);
+    std::vector<short2>().swap(L->tex_xy);
+    std::vector<float>().swap(L->tex_ori);
+    std::vector<float>().swap(L->tex_des);
+    return LAFIS_OK;
+}
+
+int lafis_latents_from_packed(lafis_ctx* c, const lafis_packed_latents* p, lafis_latents** out) {
+    if (!c || !p || !out || p->n_latents < 0) return fail(c, LAFIS_ERR_ARG, "bad latent argument");
+    const int n = p->n_latents;
+    lafis_latents* L = new lafis_latents();
+    L->n = n;
+    L->owner = c;
+    L->status.resize(n);
+    L->tex_weighted.resize(n);
+    L->slot_n.assign(3 * n, 0);
+    L->slot_off.assign(3 * n, 0);
+    L->tex_n.assign(n, 0);
+    int max_t = 0;
+    for (int q = 0; q < n; ++q) {
+        const int nm = p->n_minu_templates[q], nt = p->n_tex_templates[q];
+        // One2One_matching_selected_templates, matcher.cpp:383-386, and the score[28] read of :188
+        int st = LAFIS_OK;
+        if (nm <= kSelected[0] && nt <= 0) st = LAFIS_LATENT_EMPTY;
+        else if (nm + nt < 29) st = LAFIS_ERR_LATENT_LAYOUT;
+        L->status[q] = st;
+        L->tex_weighted[q] = (nm == 28 && nt >= 1) ? 1 : 0;
+        int ntp = nt > 0 ? (int)(p->tex_off[q + 1] - p->tex_off[q]) : 0;
+        if (ntp > kMaxTexture) ntp = kMaxTexture;  // matcher.cpp:544-545
+        // the texture score lands in score[n_minu_templates] (matcher.cpp:414) and only score[28] is
+        // fused (:188): with any other template count it is never read, so it is not computed
+        if (!L->tex_weighted[q]) ntp = 0;
+        L->tex_n[q] = ntp;
+        max_t = std::max(max_t, ntp);
+    }
+    L->lt_stride = std::max(8, round_up(max_t, 8));
+    uint32_t off = 0;
+    for (int s = 0; s < 3 * n; ++s) {
+        const int q = s / 3, slot = s % 3;
+        int cnt = (int)(p->minu_off[s + 1] - p->minu_off[s]);
+        if (p->n_minu_templates[q] <= kSelected[slot]) cnt = 0;  // matcher.cpp:403-404
+        if (cnt > kMaxMinutiae) {
+            delete L;
+            return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE, "latent %d: %d minutiae", q, cnt);
+        }
+        L->slot_n[s] = cnt;
+        L->slot_off[s] = off;
+        L->max_slot_n = std::max(L->max_slot_n, cnt);
+        off += (uint32_t)((cnt + 3) & ~3);
+    }
+    L->tot_minu_padded = off;
+    L->minu_xy.assign(std::max<uint32_t>(off, 4), make_short2(0, 0));
+    L->minu_ori.assign(std::max<uint32_t>(off, 4), 0.0f);
+    L->minu_desT.assign((size_t)kDesLen * std::max<uint32_t>(off, 4), 0.0f);
+    for (int s = 0; s < 3 * n; ++s) {
+        const int cnt = L->slot_n[s], np = (cnt + 3) & ~3;
+        const uint32_t so = p->minu_off[s], dof = L->slot_off[s];
+        for (int i = 0; i < cnt; ++i) {
+            L->minu_xy[dof + i] = make_short2(p->minu_x[so + i], p->minu_y[so + i]);
+            L->minu_ori[dof + i] = p->minu_ori[so + i];
+            const float* d = p->minu_des + (size_t)(so + i) * kDesLen;
+            float* T = L->minu_desT.data() + (size_t)kDesLen * dof;
+            for (int k = 0; k < kDesLen; ++k) T[(size_t)k * np + i] = d[k];
+        }
+    }
+    const size_t lt = (size_t)L->lt_stride;
+    L->tex_xy.assign(lt * std::max(n, 1), make_short2(0, 0));
+    L->tex_ori.assign(lt * std::max(n, 1), 0.0f);
+    L->tex_des.assign(lt * std::max(n, 1) * kDesLen, 0.0f);
+    for (int q = 0; q < n; ++q) {
+        const int cnt = L->tex_n[q];
+        const uint32_t so = p->tex_off[q];
+        for (int i = 0; i < cnt; ++i) {
+            L->tex_xy[q * lt + i] = make_short2(p->tex_x[so + i], p->tex_y[so + i]);
+            L->tex_ori[q * lt + i] = p->tex_ori[so + i];
+        }
+        if (cnt)
+            std::memcpy(L->tex_des.data() + (size_t)q * lt * kDesLen, p->tex_des + (size_t)so * kDesLen,
+                        sizeof(float) * (size_t)cnt * kDesLen);
+    }
+    int rc = finish_latents(c, L);
+    if (rc != LAFIS_OK) {
+        lafis_latents_free(L);
+        return rc;
+    }
+    *out = L;
+    return LAFIS_OK;
+}
+
+int lafis_latents_load_files(lafis_ctx* c, const char* const* paths, int n, lafis_latents** out) {
+    if (!c || !out || (!paths && n > 0) || n < 0) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    if (n == 0) return fail(c, LAFIS_ERR_NO_TEMPLATES, "no latent templates");
+    std::vector<int32_t> nm(n), nt(n);
+    std::vector<uint32_t> minu_off(3 * n + 1, 0), tex_off(n + 1, 0);
+    std::vector<int16_t> mx, my, tx, ty;
+    std::vector<float> mori, mdes, tori, tdes;
+    for (int q = 0; q < n; ++q) {
+        LatentTemplate T;
+        read_latent_dat(paths[q], T);  // the drivers ignore the loader's return code (matcher.cpp:150, :259)
+        nm[q] = T.n_minu_templates;
+        nt[q] = T.n_tex_templates;
+        for (int s = 0; s < 3; ++s) {
+            const PointSet& P = T.minu[s];
+            mx.insert(mx.end(), P.x.begin(), P.x.end());
+            my.insert(my.end(), P.y.begin(), P.y.end());
+            mori.insert(mori.end(), P.ori.begin(), P.ori.end());
+            mdes.insert(mdes.end(), P.des.begin(), P.des.end());
+            minu_off[3 * q + s + 1] = (uint32_t)mx.size();
+        }
+        tx.insert(tx.end(), T.tex.x.begin(), T.tex.x.end());
+        ty.insert(ty.end(), T.tex.y.begin(), T.tex.y.end());
+        tori.insert(tori.end(), T.tex.ori.begin(), T.tex.ori.end());
+        tdes.insert(tdes.end(), T.tex.des.begin(), T.tex.des.end());
+        tex_off[q + 1] = (uint32_t)tx.size();
+    }
+    lafis_packed_latents p{};
+    p.n_latents = n;
+    p.n_minu_templates = nm.data();
+    p.n_tex_templates = nt.data();
+    p.minu_off = minu_off.data();
+    p.minu_x = mx.data();
+    p.minu_y = my.data();
+    p.minu_ori = mori.data();
+    p.minu_des = mdes.data();
+    p.tex_off = tex_off.data();
+    p.tex_x = tx.data();
+    p.tex_y = ty.data();
+    p.tex_ori = tori.data();
+    p.tex_des = tdes.data();
+    return lafis_latents_from_packed(c, &p, out);
+}
+
+int lafis_latents_count(const lafis_latents* l) { return l ? l->n : 0; }
+int lafis_latents_status(const lafis_latents* l, int q) {
+    return (l && q >= 0 && q < l->n) ? l->status[q] : LAFIS_ERR_ARG;
+}
+
+void lafis_latents_free(lafis_latents* l) {
+    if (!l) return;
+    if (l->owner) cudaSetDevice(l->owner->device);
+    if (l->d_arena) {
+        if (l->owner && l->owner->stream) cudaStreamSynchronize(l->owner->stream);
+        cudaFree(l->d_arena);
+    }
+    if (l->pinned) cudaFreeHost(l->pinned);
+    delete l;
+}
+
+int lafis_latents_make_resident(lafis_ctx* c, lafis_latents* l) {
+    if (!c || !l) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    if (!l->d_arena) LAFIS_CUDA(c, cudaMalloc(&l->d_arena, std::max<size_t>(l->arena_bytes, 256)));
+    LAFIS_CUDA(c, cudaMemcpyAsync(l->d_arena, l->pinned, l->arena_bytes, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    l->resident = true;
+    l->owner = c;
+    return LAFIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------------------
+static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
+    const int Q = L->n, G = c->gal.n;
+    if (G <= 0) return fail(c, LAFIS_ERR_NO_GALLERY, "no gallery resident");
+    if (Q <= 0) return fail(c, LAFIS_ERR_ARG, "empty latent batch");
+    if (topk < 0 || topk > kTopkChunk / 2) return fail(c, LAFIS_ERR_ARG, "topk must be in [0, %d]", kTopkChunk / 2);
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+
+    // ---- latent batch in HBM ----
+    unsigned char* A = nullptr;
+    if (L->resident && L->owner == c) {
+        A = L->d_arena;
+    } else {
+        LAFIS_CUDA(c, c->lat_arena.reserve(L->arena_bytes));
+        A = c->lat_arena.p;
+    }
+    LAFIS_CUDA(c, cudaEventRecord(c->ev0, st));
+    if (A != L->d_arena) LAFIS_CUDA(c, cudaMemcpyAsync(A, L->pinned, L->arena_bytes, cudaMemcpyHostToDevice, st));
+    DeviceLatents D;
+    D.n = Q;
+    D.lt_stride = L->lt_stride;
+    D.slot_n = reinterpret_cast<int*>(A + L->o_slot_n);
+    D.slot_off = reinterpret_cast<uint32_t*>(A + L->o_slot_off);
+    D.minu_xy = reinterpret_cast<short2*>(A + L->o_minu_xy);
+    D.minu_ori = reinterpret_cast<float*>(A + L->o_minu_ori);
+    D.minu_desT = reinterpret_cast<float*>(A + L->o_minu_desT);
+    D.tex_n = reinterpret_cast<int*>(A + L->o_tex_n);
+    D.tex_xy = reinterpret_cast<short2*>(A + L->o_tex_xy);
+    D.tex_ori = reinterpret_cast<float*>(A + L->o_tex_ori);
+    D.tex_des = reinterpret_cast<float*>(A + L->o_tex_des);
+    D.tex_weighted = reinterpret_cast<int*>(A + L->o_weighted);
+    D.status = reinterpret_cast<int*>(A + L->o_status);
+
+    // ---- geometry ----
+    const int nLs = std::max(32, round_up(L->max_slot_n, 32)), nRs = std::max(32, round_up(c->max_nR, 32));
+    const size_t corr_smem = minu_corr_smem_bytes(nLs, nRs);
+    if (corr_smem > (size_t)kCorrMaxDynSmem || (size_t)nLs * nRs >= 65536)
+        return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE,
+                    "minutiae templates of %d x %d points need %zu bytes of shared memory (limit %d)",
+                    L->max_slot_n, c->max_nR, corr_smem, kCorrMaxDynSmem);
+    const size_t lt = (size_t)L->lt_stride;
+    const size_t per_tpl = (size_t)Q * (lt * 6 + 3 * (kTopCorrMinu * 8 + 4));
+    size_t chunk_sz = std::max<size_t>(1, c->work_budget / std::max<size_t>(per_tpl, 1));
+    chunk_sz = std::min<size_t>(chunk_sz, (size_t)G);
+    // keep every grid dimension and flat index comfortably inside 31 bits
+    chunk_sz = std::min<size_t>(chunk_sz, (size_t)0x7fffffff / ((size_t)Q * 3 * kTopCorrMinu));
+    chunk_sz = std::max<size_t>(chunk_sz, 1);
+    const int n_chunk_max = (int)chunk_sz;
+
+    LAFIS_CUDA(c, c->rowmax_val.reserve((size_t)Q * n_chunk_max * lt));
+    LAFIS_CUDA(c, c->rowmax_j.reserve((size_t)Q * n_chunk_max * lt));
+    LAFIS_CUDA(c, c->corr_v.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
+    LAFIS_CUDA(c, c->corr_ij.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
+    LAFIS_CUDA(c, c->corr_n.reserve((size_t)Q * n_chunk_max * 3));
+    LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
+    LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
+
+    const bool prof = c->profile;
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto stamp = [&](int i) {
+        if (prof) cudaEventRecord(c->evs[i], st);
+    };
+    auto lap = [&](int stage, int a, int b) {
+        if (!prof) return;
+        float ms = 0;
+        cudaEventSynchronize(c->evs[b]);
+        cudaEventElapsedTime(&ms, c->evs[a], c->evs[b]);
+        stage_ms[stage] += ms;
+    };
+
+    for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
+        const int n_chunk = std::min(n_chunk_max, G - g0);
+        // ---- K1 + K2 + K3a ----
+        stamp(0);
+        {
+            TexRowmaxParams P;
+            P.lat_des = D.tex_des;
+            P.lat_nt = D.tex_n;
+            P.lt_stride = L->lt_stride;
+            P.Q = Q;
+            P.codebook = c->d_codebook;
+            P.tex_off = c->gal.tex_off;
+            P.codes = c->gal.tex_codes;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            const int n_rowtiles = L->lt_stride / kRowTile;
+            const int want_jobs = 4 * c->sm_count;
+            int slices = (want_jobs + Q * n_rowtiles - 1) / (Q * n_rowtiles);
+            slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
+            P.slices = slices;
+            P.rowmax_val = c->rowmax_val.p;
+            P.rowmax_j = c->rowmax_j.p;
+            P.job_counter = c->d_job_counter;
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_job_counter, 0, sizeof(int), st));
+            const int grid = std::min(c->sm_count, Q * n_rowtiles * slices);
+            tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, st>>>(P);
+        }
+        stamp(1);
+        // ---- K5 + K6 + K7 ----
+        {
+            MinuCorrParams P;
+            P.slot_n = D.slot_n;
+            P.slot_off = D.slot_off;
+            P.lat_desT = D.minu_desT;
+            P.lat_status = D.status;
+            P.Q = Q;
+            P.minu_off = c->gal.minu_off;
+            P.minu_n = c->gal.minu_n;
+            P.minu_desT = c->gal.minu_desT;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            P.nLs = nLs;
+            P.nRs = nRs;
+            P.corr_v = c->corr_v.p;
+            P.corr_ij = c->corr_ij.p;
+            P.corr_n = c->corr_n.p;
+            P.slow_path_count = c->d_slow;
+            minu_corr_kernel<<<n_chunk, kCorrThreads, corr_smem, st>>>(P);
+        }
+        stamp(2);
+        // ---- K8 + K9 (minutiae) ----
+        {
+            GraphMinuParams P;
+            P.corr_v = c->corr_v.p;
+            P.corr_ij = c->corr_ij.p;
+            P.corr_n = c->corr_n.p;
+            P.slot_off = D.slot_off;
+            P.lat_xy = D.minu_xy;
+            P.lat_ori = D.minu_ori;
+            P.minu_off = c->gal.minu_off;
+            P.gal_xy = c->gal.minu_xy;
+            P.gal_ori = c->gal.minu_ori;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            P.G = G;
+            P.comp = c->comp.p;
+            const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
+            graph_minu_kernel<<<grid, kGraphMinuThreads, kGraphMinuSmem, st>>>(P);
+        }
+        stamp(3);
+        // ---- K3b + K4 + K9 (texture) ----
+        {
+            GraphTexParams P;
+            P.rowmax_val = c->rowmax_val.p;
+            P.rowmax_j = c->rowmax_j.p;
+            P.lt_stride = L->lt_stride;
+            P.lat_nt = D.tex_n;
+            P.lat_status = D.status;
+            P.lat_xy = D.tex_xy;
+            P.lat_ori = D.tex_ori;
+            P.tex_off = c->gal.tex_off;
+            P.gal_xy = c->gal.tex_xy;
+            P.gal_ori = c->gal.tex_ori;
+            P.table = c->d_table;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            P.G = G;
+            P.comp = c->comp.p;
+            P.slow_path_count = c->d_slow + 1;
+            const unsigned grid = (unsigned)((size_t)Q * n_chunk);
+            graph_tex_kernel<<<grid, kGraphTexThreads, kGraphTexSmem, st>>>(P);
+        }
+        stamp(4);
+        c->stats.kernel_launches += 4;
+        LAFIS_CUDA(c, cudaGetLastError());
+        lap(0, 0, 1);
+        lap(1, 1, 2);
+        lap(2, 2, 3);
+        lap(3, 3, 4);
+    }
+
+    // ---- K10 ----
+    stamp(5);
+    {
+        FuseParams P;
+        P.comp = c->comp.p;
+        P.lat_status = D.status;
+        P.tex_weighted = D.tex_weighted;
+        P.gal_status = c->gal.status;
+        P.Q = Q;
+        P.G = G;
+        P.final_scores = c->final_scores.p;
+        const size_t tot = (size_t)Q * G;
+        fuse_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P);
+        c->stats.kernel_launches += 1;
+    }
+    // ---- K11: rank lists ----
+    if (topk > 0) {
+        int chunks = (G + kTopkChunk - 1) / kTopkChunk;
+        LAFIS_CUDA(c, c->keys_a.reserve((size_t)Q * chunks * topk));
+        LAFIS_CUDA(c, c->hits.reserve((size_t)Q * topk));
+        topk_scores_kernel<<<dim3(chunks, Q), kTopkThreads, 0, st>>>(c->final_scores.p, G, c->index_base, topk,
+                                                                      c->keys_a.p);
+        c->stats.kernel_launches += 1;
+        unsigned long long* cur = c->keys_a.p;
+        int n_in = chunks * topk;
+        bool use_b = true;
+        while (n_in > topk) {
+            const int chunks2 = (n_in + kTopkChunk - 1) / kTopkChunk;
+            DevBuf<unsigned long long>& dst = use_b ? c->keys_b : c->keys_a;
+            LAFIS_CUDA(c, dst.reserve((size_t)Q * chunks2 * topk));
+            topk_keys_kernel<<<dim3(chunks2, Q), kTopkThreads, 0, st>>>(cur, n_in, topk, dst.p);
+            c->stats.kernel_launches += 1;
+            cur = dst.p;
+            n_in = chunks2 * topk;
+            use_b = !use_b;
+            if (chunks2 == 1) break;
+        }
+        const size_t nh = (size_t)Q * topk;
+        keys_to_hits_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(cur, nh, c->hits.p);
+        c->stats.kernel_launches += 1;
+    }
+    stamp(6);
+    LAFIS_CUDA(c, cudaGetLastError());
+    LAFIS_CUDA(c, cudaEventRecord(c->ev1, st));
+    lap(4, 5, 6);
+    c->stats.pairs_scored += (uint64_t)Q * G;
+    if (prof) std::memcpy(c->stats.last_stage_ms, stage_ms, sizeof stage_ms);
+    return LAFIS_OK;
+}
+
+int lafis_match_device(lafis_ctx* c, lafis_latents* L, int topk, const void** d_hits, const float** d_all_scores) {
+    if (!c || !L) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    int rc = run_match(c, L, topk);
+    if (rc != LAFIS_OK) return rc;
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
+    if (d_hits) *d_hits = topk > 0 ? (const void*)c->hits.p : nullptr;
+    if (d_all_scores) *d_all_scores = c->final_scores.p;
+    return LAFIS_OK;
+}
+
+int lafis_match(lafis_ctx* c, lafis_latents* L, int topk, lafis_hit* hits, float* all_scores, float* components) {
+    if (!c || !L) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    if (!hits) topk = 0;
+    int rc = run_match(c, L, topk);
+    if (rc != LAFIS_OK) return rc;
+    const size_t QG = (size_t)L->n * c->gal.n;
+    if (hits && topk > 0)
+        LAFIS_CUDA(c, cudaMemcpyAsync(hits, c->hits.p, sizeof(lafis_hit) * (size_t)L->n * topk, cudaMemcpyDeviceToHost,
+                                      c->stream));
+    if (all_scores)
+        LAFIS_CUDA(c, cudaMemcpyAsync(all_scores, c->final_scores.p, sizeof(float) * QG, cudaMemcpyDeviceToHost, c->stream));
+    if (components)
+        LAFIS_CUDA(c, cudaMemcpyAsync(components, c->comp.p, sizeof(float) * QG * 4, cudaMemcpyDeviceToHost, c->stream));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
+    return LAFIS_OK;
+}
+
+int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n_lists, int topk, lafis_hit* out) {
+    if (!shard_hits || !out || n_latents < 0 || n_lists <= 0 || topk <= 0) return LAFIS_ERR_ARG;
+    std::vector<lafis_hit> all((size_t)n_lists * topk);
+    for (int q = 0; q < n_latents; ++q) {
+        const lafis_hit* src = shard_hits + (size_t)q * n_lists * topk;
+        all.assign(src, src + (size_t)n_lists * topk);
+        std::sort(all.begin(), all.end(), [](const lafis_hit& a, const lafis_hit& b) {
+            const bool ae = a.index == 0xffffffffu, be = b.index == 0xffffffffu;  // empty slots last
+            if (ae != be) return be;
+            if (a.score != b.score) return a.score > b.score;
+            return a.index < b.index;
+        });
+        std::copy(all.begin(), all.begin() + topk, out + (size_t)q * topk);
+    }
+    return LAFIS_OK;
+}
+
+int lafis_pq_encode(lafis_ctx* c, const float* des, int64_t n, uint8_t* codes, int on_device) {
+    if (!c || !des || !codes || n < 0) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    if (n == 0) return LAFIS_OK;
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    const float* d_des = des;
+    uint8_t* d_codes = codes;
+    float* tmp_des = nullptr;
+    uint8_t* tmp_codes = nullptr;
+    if (!on_device) {
+        LAFIS_CUDA(c, cudaMalloc(&tmp_des, sizeof(float) * kDesLen * (size_t)n));
+        if (cudaMalloc(&tmp_codes, (size_t)n * kSubs) != cudaSuccess) {
+            cudaFree(tmp_des);
+            return fail(c, LAFIS_ERR_CUDA, "cudaMalloc failed");
+        }
+        cudaMemcpyAsync(tmp_des, des, sizeof(float) * kDesLen * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        d_des = tmp_des;
+        d_codes = tmp_codes;
+    }
+    const int pts_per_block = 256 / 16;
+    pq_encode_kernel<<<(unsigned)((n + pts_per_block - 1) / pts_per_block), 256, 0, c->stream>>>(d_des, (long long)n,
+                                                                                               c->d_codebook, d_codes);
+    c->stats.kernel_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !on_device)
+        e = cudaMemcpyAsync(codes, tmp_codes, (size_t)n * kSubs, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp_des);
+    cudaFree(tmp_codes);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(c, LAFIS_ERR_CUDA, "pq_encode failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return LAFIS_OK;
+}
+
+}  // extern "C"

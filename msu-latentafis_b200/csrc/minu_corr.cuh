@@ -26,6 +26,7 @@ namespace lafis {
 
 constexpr int kCorrThreads = 512;
 constexpr int kHistBins = 4096;
+constexpr int kCorrMaxDynSmem = 227 * 1024 - 2048;  // the kernel also holds ~1 KB of static shared memory
 
 struct MinuCorrParams {
     // latent side
@@ -45,9 +46,6 @@ struct MinuCorrParams {
     float* corr_v;        // x120
     uint32_t* corr_ij;    // x120, (i << 16) | j
     int* corr_n;
-    // per-CTA scratch for the introsort replay: [gridDim.x][scratch_stride] ints
-    int* scratch;
-    int scratch_stride;
     unsigned long long* slow_path_count;  // statistics
 };
 
@@ -97,7 +95,7 @@ __device__ __forceinline__ int find_bin_warp(const int* hist, int nbins, int nee
 }
 
 __global__ void __launch_bounds__(kCorrThreads, 1) minu_corr_kernel(MinuCorrParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int nLs = P.nLs, nRs = P.nRs, ldS = nRs + 1;
     float* A_T = reinterpret_cast<float*>(smem);          // [96][nLs]
     float* B_T = A_T + 96 * nLs;                           // [96][nRs]
@@ -118,14 +116,24 @@ __global__ void __launch_bounds__(kCorrThreads, 1) minu_corr_kernel(MinuCorrPara
     uint32_t* keys = reinterpret_cast<uint32_t*>(S);
 
     // ---- stage B_T (zero padded to nRs columns) ----
-    if (nR > 0) {
+    auto stage_B = [&]() {
+        if (nR <= 0) return;
         const int nRp = (nR + 3) & ~3;
         const float* src = P.minu_desT + (size_t)96 * P.minu_off[g];
         for (int e = tid; e < 96 * nRs; e += kCorrThreads) {
             const int k = e / nRs, j = e - k * nRs;
             B_T[e] = (j < nR) ? __ldg(src + (size_t)k * nRp + j) : 0.0f;
         }
-    }
+    };
+    auto stage_A = [&](int q, int slot, int nL) {
+        const int nLp = (nL + 3) & ~3;
+        const float* src = P.lat_desT + (size_t)96 * P.slot_off[q * 3 + slot];
+        for (int e = tid; e < 96 * nLs; e += kCorrThreads) {
+            const int k = e / nLs, i = e - k * nLs;
+            A_T[e] = (i < nL) ? __ldg(src + (size_t)k * nLp + i) : 0.0f;
+        }
+    };
+    stage_B();
 
     for (int q = 0; q < P.Q; ++q) {
         for (int slot = 0; slot < 3; ++slot) {
@@ -136,14 +144,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) minu_corr_kernel(MinuCorrPara
                 continue;
             }
             __syncthreads();  // previous slot done with A_T / S
-            {   // stage A_T (zero padded)
-                const int nLp = (nL + 3) & ~3;
-                const float* src = P.lat_desT + (size_t)96 * P.slot_off[q * 3 + slot];
-                for (int e = tid; e < 96 * nLs; e += kCorrThreads) {
-                    const int k = e / nLs, i = e - k * nLs;
-                    A_T[e] = (i < nL) ? __ldg(src + (size_t)k * nLp + i) : 0.0f;
-                }
-            }
+            stage_A(q, slot, nL);
             __syncthreads();
 
             // ---- K5 ----
@@ -308,17 +309,23 @@ __global__ void __launch_bounds__(kCorrThreads, 1) minu_corr_kernel(MinuCorrPara
             }
             __syncthreads();
             if (boundary_tie || s_flag) {
-                // replay libstdc++'s introsort over all M indices (rare)
+                // Replay libstdc++'s introsort (rare).  The index array (u16, M < 65536) borrows the
+                // A_T/B_T staging area, which is re-staged afterwards.
                 if (tid == 0) {
-                    int* y = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
-                    // keys live with row stride ldS; the emulation needs a dense key array: compact
-                    // them behind the index array in the same scratch block
-                    uint32_t* dense = reinterpret_cast<uint32_t*>(y + M);
-                    for (int e = 0; e < M; ++e) dense[e] = keys[(size_t)(e / nR) * ldS + (e % nR)];
-                    std_sort_desc_emulate<uint32_t, int>(dense, y, M);
-                    for (int r = 0; r < K; ++r) s_order[r] = y[r];
+                    uint16_t* y = reinterpret_cast<uint16_t*>(A_T);
+                    const uint32_t* kk = keys;
+                    const int nRr = nR, ld = ldS;
+                    auto keyfn = [kk, nRr, ld](int e) -> uint32_t {
+                        const int i = e / nRr;
+                        return kk[i * ld + (e - i * nRr)];
+                    };
+                    std_sort_desc_prefix(keyfn, y, M, K);
+                    for (int r = 0; r < K; ++r) s_order[r] = (int)y[r];
                     atomicAdd(P.slow_path_count, 1ull);
                 }
+                __syncthreads();
+                stage_B();
+                stage_A(q, slot, nL);
                 __syncthreads();
             }
 

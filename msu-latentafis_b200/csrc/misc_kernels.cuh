@@ -196,9 +196,40 @@ __global__ void relayout_minutiae_kernel(RelayoutParams P) {
     }
 }
 
-__global__ void pack_xy_kernel(const int16_t* x, const int16_t* y, size_t n, short2* out) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) out[e] = make_short2(x[e], y[e]);
+// texture template g: points [src_off[g], src_off[g] + n) with n = dst_off[g+1] - dst_off[g]
+// (<= 1000, matcher.cpp:546-547) -> packed coordinates, orientations and 16-byte code words.
+struct TexCopyParams {
+    const uint32_t* src_off;
+    const uint32_t* dst_off;
+    const int16_t* x;
+    const int16_t* y;
+    const float* ori;
+    const uint4* codes;
+    bool codes_aligned;
+    short2* out_xy;
+    float* out_ori;
+    uint4* out_codes;
+};
+
+__global__ void copy_texture_kernel(TexCopyParams P) {
+    const int g = blockIdx.x;
+    const uint32_t s0 = P.src_off[g], d0 = P.dst_off[g], n = P.dst_off[g + 1] - d0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        P.out_xy[d0 + i] = make_short2(P.x[s0 + i], P.y[s0 + i]);
+        P.out_ori[d0 + i] = P.ori[s0 + i];
+        uint4 c;
+        if (P.codes_aligned) {
+            c = P.codes[s0 + i];
+        } else {
+            const uint8_t* b = reinterpret_cast<const uint8_t*>(P.codes) + (size_t)(s0 + i) * 16;
+            uint32_t w[4];
+            for (int k = 0; k < 4; ++k)
+                w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) |
+                       ((uint32_t)b[4 * k + 3] << 24);
+            c = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        P.out_codes[d0 + i] = c;
+    }
 }
 
 }  // namespace lafis

@@ -9,7 +9,16 @@
 // (median-of-3 to first, unguarded Hoare partition, recursion on the right part, depth limit
 // 2*floor(log2 n) with heap-sort fallback, final insertion sort with threshold 16) step for step.
 // For n <= 16 std::sort is a plain insertion sort, i.e. stable, and the total order is already
-// exact.  Host+device so that tests/test_stdsort.py can pin it against std::sort on the CPU.
+// exact.
+//
+// Prefix replay.  Every caller only consumes the first `need` positions of the sorted sequence
+// (top-120 / top-200 / the greedy pass).  After a partition step the right part [cut, last) holds
+// keys <= pivot <= every key of the left part, and neither the later partition steps nor the final
+// insertion pass (which moves an element left only past strictly smaller keys) ever carry an
+// element across `cut`.  So partitions that start at or beyond `need` cannot influence positions
+// [0, need) and are skipped; the replay costs O(n) instead of O(n log n).
+//
+// Host+device so that tests/test_host_math.py can pin it against std::sort on the CPU.
 #pragma once
 #include <stdint.h>
 
@@ -21,12 +30,13 @@
 
 namespace lafis {
 
-template <typename KeyT, typename IdxT>
+// KeyFn: key(index) -> comparable value.  IdxT: integer type of the index array.
+template <typename KeyFn, typename IdxT>
 struct StdSortEmu {
-    const KeyT* key;
+    KeyFn key;
     IdxT* y;
 
-    LAFIS_SORT_HD bool before(IdxT a, IdxT b) const { return key[a] > key[b]; }
+    LAFIS_SORT_HD bool before(IdxT a, IdxT b) const { return key((int)a) > key((int)b); }
     LAFIS_SORT_HD void swp(int a, int b) {
         IdxT t = y[a];
         y[a] = y[b];
@@ -117,22 +127,25 @@ struct StdSortEmu {
             ++lo;
         }
     }
-    // y must hold 0..n-1 on entry (std::iota)
-    LAFIS_SORT_HD void sort(int n) {
+    // y must hold 0..n-1 on entry (std::iota).  On return positions [0, min(need, n)) are what
+    // std::sort leaves there; later positions are unspecified.
+    LAFIS_SORT_HD void sort_prefix(int n, int need) {
         if (n <= 0) return;
+        if (need > n) need = n;
         int lg = 0;
         for (int m = n; m > 1; m >>= 1) ++lg;
-        // __introsort_loop: recursion on [cut,last) happens BEFORE the loop continues on
-        // [first,cut); the partitions are disjoint, so an explicit stack of deferred left parts
-        // visits them with identical contents (order of processing does not change the result).
+        // __introsort_loop recurses into [cut,last) and continues on [first,cut); the two parts are
+        // disjoint, so an explicit stack of deferred parts visits them with identical contents.
         struct Frame {
             int first, last, depth;
         };
-        Frame stack[64];
+        Frame stack[72];
         int sp = 0;
+        int done_to = 0;  // positions [0, done_to) belong to fully partitioned (or heap-sorted) ranges
         stack[sp++] = Frame{0, n, 2 * lg};
         while (sp > 0) {
             Frame f = stack[--sp];
+            if (f.first >= need) continue;
             while (f.last - f.first > 16) {
                 if (f.depth == 0) {
                     heap_sort(f.first, f.last);
@@ -140,24 +153,44 @@ struct StdSortEmu {
                 }
                 --f.depth;
                 const int cut = partition_pivot(f.first, f.last);
-                if (sp < 64) stack[sp++] = Frame{f.first, cut, f.depth};  // the loop's continuation
-                f.first = cut;                                               // the recursive call
+                if (cut < need) stack[sp++] = Frame{cut, f.last, f.depth};  // the recursive call
+                f.last = cut;                                                // the loop's continuation
             }
+            if (f.last > done_to) done_to = f.last;
         }
         if (n > 16) {
+            // the leaf ranges with first < need tile [0, E) contiguously, so E >= need
+            int E = done_to;
+            if (E < 16) E = 16;
+            if (E > n) E = n;
             insertion_sort(0, 16);
-            for (int i = 16; i != n; ++i) unguarded_linear_insert(i);
+            for (int i = 16; i < E; ++i) unguarded_linear_insert(i);
         } else {
             insertion_sort(0, n);
         }
     }
 };
 
+template <typename KeyT>
+struct DenseKey {
+    const KeyT* k;
+    LAFIS_SORT_HD KeyT operator()(int i) const { return k[i]; }
+};
+
+// full permutation (need = n)
 template <typename KeyT, typename IdxT>
 LAFIS_SORT_HD inline void std_sort_desc_emulate(const KeyT* key, IdxT* y, int n) {
     for (int i = 0; i < n; ++i) y[i] = (IdxT)i;
-    StdSortEmu<KeyT, IdxT> s{key, y};
-    s.sort(n);
+    StdSortEmu<DenseKey<KeyT>, IdxT> s{DenseKey<KeyT>{key}, y};
+    s.sort_prefix(n, n);
+}
+
+// first `need` positions only
+template <typename KeyFn, typename IdxT>
+LAFIS_SORT_HD inline void std_sort_desc_prefix(KeyFn key, IdxT* y, int n, int need) {
+    for (int i = 0; i < n; ++i) y[i] = (IdxT)i;
+    StdSortEmu<KeyFn, IdxT> s{key, y};
+    s.sort_prefix(n, need);
 }
 
 }  // namespace lafis

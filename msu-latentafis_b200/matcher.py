@@ -1,0 +1,428 @@
+"""Python mirror of the reference's in-process matcher surface `PQ::Matcher`
+(matching/matcher.h:34-75) on top of the C ABI of `include/latentafis_b200.h`.
+
+`Matcher(code_file)`, `One2List_matching(latent_file, rolled_dir, score_path)` and
+`List2List_matching(latent_dir, rolled_dir, score_path)` keep the reference's names, argument meaning,
+return codes and score-file formats (matching/matcher.cpp:31, :96, :216).  The gallery-resident API
+(`set_gallery`, `load_gallery_dir`, `match`) is what the drivers are built on.  Everything that
+computes goes through `lib/liblatentafis_b200.so`; there is no Python or CPU implementation of any
+scoring stage, and construction fails when the library or an sm_100 device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import templates as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liblatentafis_b200.so")
+
+LAFIS_OK = 0
+LAFIS_LATENT_EMPTY = 1
+LAFIS_ERR_NO_TEMPLATES = -1
+LAFIS_ERR_ARG = -2
+LAFIS_ERR_IO = -3
+LAFIS_ERR_CODEBOOK = -4
+LAFIS_ERR_CUDA = -5
+LAFIS_ERR_UNSUPPORTED_SIZE = -6
+LAFIS_ERR_LATENT_LAYOUT = -7
+LAFIS_ERR_NO_GALLERY = -8
+
+SELECTED = (26, 2, 11)  # matching/matcher.cpp:380
+
+HIT_DTYPE = np.dtype([("score", "<f4"), ("index", "<u4")])
+
+
+class LafisError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"latentafis_b200 status {status}: {message}")
+        self.status = status
+
+
+class _PackedGallery(C.Structure):
+    _fields_ = [("n_templates", C.c_int32), ("minu_off", C.c_void_p), ("minu_x", C.c_void_p), ("minu_y", C.c_void_p),
+                ("minu_ori", C.c_void_p), ("minu_des", C.c_void_p), ("tex_off", C.c_void_p), ("tex_x", C.c_void_p),
+                ("tex_y", C.c_void_p), ("tex_ori", C.c_void_p), ("tex_codes", C.c_void_p), ("status", C.c_void_p),
+                ("on_device", C.c_int32)]
+
+
+class _PackedLatents(C.Structure):
+    _fields_ = [("n_latents", C.c_int32), ("n_minu_templates", C.c_void_p), ("n_tex_templates", C.c_void_p),
+                ("minu_off", C.c_void_p), ("minu_x", C.c_void_p), ("minu_y", C.c_void_p), ("minu_ori", C.c_void_p),
+                ("minu_des", C.c_void_p), ("tex_off", C.c_void_p), ("tex_x", C.c_void_p), ("tex_y", C.c_void_p),
+                ("tex_ori", C.c_void_p), ("tex_des", C.c_void_p)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("pairs_scored", C.c_uint64), ("last_match_ms", C.c_float),
+                ("last_stage_ms", C.c_float * 8)]
+
+
+_lib = None
+
+EXPORTS = [
+    "lafis_create", "lafis_create_from_codebook", "lafis_destroy", "lafis_last_error", "lafis_version",
+    "lafis_gallery_load_dir", "lafis_gallery_load_files", "lafis_gallery_set_packed", "lafis_gallery_size",
+    "lafis_gallery_path", "lafis_gallery_status", "lafis_gallery_bytes", "lafis_gallery_get_template",
+    "lafis_latents_load_files", "lafis_latents_from_packed", "lafis_latents_count", "lafis_latents_status",
+    "lafis_latents_free", "lafis_latents_make_resident", "lafis_match", "lafis_match_device", "lafis_merge_hits",
+    "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
+    "lafis_get_stats", "lafis_stream",
+]
+
+
+def load_library():
+    """dlopen the native library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise LafisError(LAFIS_ERR_CUDA, f"{LIB_PATH} is missing: run `python msu-latentafis_b200/build.py` "
+                                         "(or __graft_entry__.build()); there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cp = C.c_void_p, C.c_int, C.c_char_p
+    L.lafis_create.argtypes = [cp, ci, C.POINTER(vp)]
+    L.lafis_create_from_codebook.argtypes = [vp, ci, ci, ci, ci, C.POINTER(vp)]
+    L.lafis_destroy.argtypes = [vp]
+    L.lafis_destroy.restype = None
+    L.lafis_last_error.argtypes = [vp]
+    L.lafis_last_error.restype = cp
+    L.lafis_version.restype = cp
+    L.lafis_gallery_load_dir.argtypes = [vp, cp, ci, ci]
+    L.lafis_gallery_load_files.argtypes = [vp, C.POINTER(cp), ci, ci, ci]
+    L.lafis_gallery_set_packed.argtypes = [vp, C.POINTER(_PackedGallery), C.c_uint32]
+    L.lafis_gallery_size.argtypes = [vp]
+    L.lafis_gallery_path.argtypes = [vp, ci]
+    L.lafis_gallery_path.restype = cp
+    L.lafis_gallery_status.argtypes = [vp, ci]
+    L.lafis_gallery_bytes.argtypes = [vp]
+    L.lafis_gallery_bytes.restype = C.c_uint64
+    L.lafis_gallery_get_template.argtypes = [vp, ci] + [vp] * 10
+    L.lafis_latents_load_files.argtypes = [vp, C.POINTER(cp), ci, C.POINTER(vp)]
+    L.lafis_latents_from_packed.argtypes = [vp, C.POINTER(_PackedLatents), C.POINTER(vp)]
+    L.lafis_latents_count.argtypes = [vp]
+    L.lafis_latents_status.argtypes = [vp, ci]
+    L.lafis_latents_free.argtypes = [vp]
+    L.lafis_latents_free.restype = None
+    L.lafis_latents_make_resident.argtypes = [vp, vp]
+    L.lafis_match.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.lafis_match_device.argtypes = [vp, vp, ci, C.POINTER(vp), C.POINTER(vp)]
+    L.lafis_merge_hits.argtypes = [vp, ci, ci, ci, vp]
+    L.lafis_one2list_matching.argtypes = [vp, cp, cp, cp]
+    L.lafis_list2list_matching.argtypes = [vp, cp, cp, cp]
+    L.lafis_forget_gallery_dir.argtypes = [vp]
+    L.lafis_forget_gallery_dir.restype = None
+    L.lafis_pq_encode.argtypes = [vp, vp, C.c_int64, vp, ci]
+    L.lafis_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.lafis_stream.argtypes = [vp]
+    L.lafis_stream.restype = vp
+    _lib = L
+    return L
+
+
+# --------------------------------------------------------------------------------------------------
+# packed host-side containers
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class PackedGallery:
+    """Structure-of-arrays gallery (`lafis_packed_gallery`).  Arrays are numpy (host) or raw device
+    pointers (ints) when `on_device` is set; offsets/status are always numpy."""
+    minu_off: np.ndarray
+    minu_x: object
+    minu_y: object
+    minu_ori: object
+    minu_des: object
+    tex_off: np.ndarray
+    tex_x: object
+    tex_y: object
+    tex_ori: object
+    tex_codes: object
+    status: Optional[np.ndarray] = None
+    on_device: bool = False
+    keepalive: object = None
+
+    @property
+    def n(self) -> int:
+        return int(self.minu_off.shape[0]) - 1
+
+
+@dataclass
+class PackedLatents:
+    n_minu_templates: np.ndarray
+    n_tex_templates: np.ndarray
+    minu_off: np.ndarray
+    minu_x: np.ndarray
+    minu_y: np.ndarray
+    minu_ori: np.ndarray
+    minu_des: np.ndarray
+    tex_off: np.ndarray
+    tex_x: np.ndarray
+    tex_y: np.ndarray
+    tex_ori: np.ndarray
+    tex_des: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.n_minu_templates.shape[0])
+
+
+def _cat(parts, dtype, width=None):
+    if not parts:
+        return np.zeros((0,) if width is None else (0, width), dtype)
+    return np.ascontiguousarray(np.concatenate(parts), dtype)
+
+
+def pack_rolled(templates: Sequence[T.FPTemplate]) -> PackedGallery:
+    """FPTemplate objects -> packed gallery, keeping what the matcher reads: minutiae template 0 and
+    texture template 0 of every print (matching/matcher.cpp:406, :413)."""
+    mo, to = [0], [0]
+    mx, my, mori, mdes, tx, ty, tori, tc = [], [], [], [], [], [], [], []
+    for t in templates:
+        if t.minu:
+            m = t.minu[0]
+            mx.append(m.x); my.append(m.y); mori.append(m.ori); mdes.append(m.des.reshape(-1, T.DES_LEN))
+            mo.append(mo[-1] + m.n)
+        else:
+            mo.append(mo[-1])
+        if t.tex:
+            x = t.tex[0]
+            tx.append(x.x); ty.append(x.y); tori.append(x.ori); tc.append(x.des.reshape(-1, T.PQ_SUBS))
+            to.append(to[-1] + x.n)
+        else:
+            to.append(to[-1])
+    return PackedGallery(np.asarray(mo, np.uint32), _cat(mx, np.int16), _cat(my, np.int16), _cat(mori, np.float32),
+                         _cat(mdes, np.float32, T.DES_LEN), np.asarray(to, np.uint32), _cat(tx, np.int16),
+                         _cat(ty, np.int16), _cat(tori, np.float32), _cat(tc, np.uint8, T.PQ_SUBS))
+
+
+def pack_latents(templates: Sequence[T.FPTemplate]) -> PackedLatents:
+    """FPTemplate objects (non-empty minutiae templates in file order) -> packed latent batch with the
+    three selected minutiae templates {26, 2, 11} and texture template 0."""
+    nm, nt, mo, to = [], [], [0], [0]
+    mx, my, mori, mdes, tx, ty, tori, td = [], [], [], [], [], [], [], []
+    for t in templates:
+        minu = [m for m in t.minu if m.n > 0]
+        tex = [x for x in t.tex if x.n > 0]
+        nm.append(len(minu)); nt.append(len(tex))
+        for s in SELECTED:
+            if s < len(minu):
+                m = minu[s]
+                mx.append(m.x); my.append(m.y); mori.append(m.ori); mdes.append(m.des.reshape(-1, T.DES_LEN))
+                mo.append(mo[-1] + m.n)
+            else:
+                mo.append(mo[-1])
+        if tex:
+            x = tex[0]
+            tx.append(x.x); ty.append(x.y); tori.append(x.ori); td.append(x.des.reshape(-1, T.DES_LEN))
+            to.append(to[-1] + x.n)
+        else:
+            to.append(to[-1])
+    return PackedLatents(np.asarray(nm, np.int32), np.asarray(nt, np.int32), np.asarray(mo, np.uint32),
+                         _cat(mx, np.int16), _cat(my, np.int16), _cat(mori, np.float32), _cat(mdes, np.float32, T.DES_LEN),
+                         np.asarray(to, np.uint32), _cat(tx, np.int16), _cat(ty, np.int16), _cat(tori, np.float32),
+                         _cat(td, np.float32, T.DES_LEN))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data
+
+
+class Latents:
+    """Owner of a `lafis_latents` handle."""
+
+    def __init__(self, matcher: "Matcher", handle):
+        self.m = matcher
+        self.h = handle
+
+    @property
+    def n(self) -> int:
+        return self.m.L.lafis_latents_count(self.h)
+
+    def status(self, q: int) -> int:
+        return self.m.L.lafis_latents_status(self.h, q)
+
+    def make_resident(self) -> "Latents":
+        self.m._chk(self.m.L.lafis_latents_make_resident(self.m.ctx, self.h))
+        return self
+
+    def free(self):
+        if self.h:
+            self.m.L.lafis_latents_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.m.ctx:
+                self.free()
+        except Exception:
+            pass
+
+
+class Matcher:
+    """`PQ::Matcher` (matching/matcher.h:34-52) on one B200."""
+
+    def __init__(self, code_file: Optional[str] = None, device: int = 0, codebook: Optional[np.ndarray] = None):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        if codebook is not None:
+            cb = np.ascontiguousarray(codebook, np.float32)
+            rc = self.L.lafis_create_from_codebook(cb.ctypes.data, cb.shape[0], cb.shape[1], cb.shape[2], device,
+                                                   C.byref(self.ctx))
+        else:
+            rc = self.L.lafis_create(os.fsencode(code_file), device, C.byref(self.ctx))
+        if rc != LAFIS_OK:
+            self.ctx = C.c_void_p()
+            why = (self.L.lafis_last_error(None) or b"").decode()
+            raise LafisError(rc, f"cannot create matcher context: {why} (this library has no CPU path)")
+        self.device = device
+        self._keep = None
+
+    # ---- reference-named drivers ----
+    def One2List_matching(self, latent_template_file: str, rolled_dir: str, score_path: str) -> int:
+        return self.L.lafis_one2list_matching(self.ctx, os.fsencode(latent_template_file), os.fsencode(rolled_dir),
+                                              os.fsencode(score_path))
+
+    def List2List_matching(self, latent_dir: str, rolled_dir: str, score_path: str) -> int:
+        return self.L.lafis_list2list_matching(self.ctx, os.fsencode(latent_dir), os.fsencode(rolled_dir),
+                                               os.fsencode(score_path))
+
+    # ---- gallery ----
+    def load_gallery_dir(self, rolled_dir: str, shard_rank: int = 0, shard_count: int = 1) -> int:
+        self._chk(self.L.lafis_gallery_load_dir(self.ctx, os.fsencode(rolled_dir), shard_rank, shard_count))
+        return self.gallery_size
+
+    def load_gallery_files(self, paths: Sequence[str], shard_rank: int = 0, shard_count: int = 1) -> int:
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self._chk(self.L.lafis_gallery_load_files(self.ctx, arr, len(paths), shard_rank, shard_count))
+        return self.gallery_size
+
+    def set_gallery(self, g: PackedGallery, index_base: int = 0) -> int:
+        s = _PackedGallery(g.n, _ptr(g.minu_off), _ptr(g.minu_x), _ptr(g.minu_y), _ptr(g.minu_ori), _ptr(g.minu_des),
+                           _ptr(g.tex_off), _ptr(g.tex_x), _ptr(g.tex_y), _ptr(g.tex_ori), _ptr(g.tex_codes),
+                           _ptr(g.status), 1 if g.on_device else 0)
+        self._chk(self.L.lafis_gallery_set_packed(self.ctx, C.byref(s), index_base))
+        return self.gallery_size
+
+    @property
+    def gallery_size(self) -> int:
+        return self.L.lafis_gallery_size(self.ctx)
+
+    @property
+    def gallery_bytes(self) -> int:
+        return int(self.L.lafis_gallery_bytes(self.ctx))
+
+    def gallery_path(self, i: int) -> str:
+        return os.fsdecode(self.L.lafis_gallery_path(self.ctx, i))
+
+    def gallery_status(self, i: int) -> int:
+        return self.L.lafis_gallery_status(self.ctx, i)
+
+    def gallery_template(self, i: int) -> T.FPTemplate:
+        nm, nt = C.c_int(0), C.c_int(0)
+        self._chk(self.L.lafis_gallery_get_template(self.ctx, i, C.addressof(nm), None, None, None, None,
+                                                    C.addressof(nt), None, None, None, None))
+        mx = np.zeros(nm.value, np.int16); my = np.zeros(nm.value, np.int16); mori = np.zeros(nm.value, np.float32)
+        mdes = np.zeros((nm.value, T.DES_LEN), np.float32)
+        tx = np.zeros(nt.value, np.int16); ty = np.zeros(nt.value, np.int16); tori = np.zeros(nt.value, np.float32)
+        tc = np.zeros((nt.value, T.PQ_SUBS), np.uint8)
+        self._chk(self.L.lafis_gallery_get_template(self.ctx, i, C.addressof(nm), _ptr(mx), _ptr(my), _ptr(mori),
+                                                    _ptr(mdes), C.addressof(nt), _ptr(tx), _ptr(ty), _ptr(tori), _ptr(tc)))
+        out = T.FPTemplate(minu=[], tex=[])
+        if nm.value:
+            out.minu.append(T.MinutiaeTemplate(mx, my, mori, mdes))
+        if nt.value:
+            out.tex.append(T.TextureTemplate(tx, ty, tori, tc))
+        return out
+
+    # ---- latents ----
+    def load_latents(self, paths: Sequence[str]) -> Latents:
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        h = C.c_void_p()
+        self._chk(self.L.lafis_latents_load_files(self.ctx, arr, len(paths), C.byref(h)))
+        return Latents(self, h)
+
+    def latents_from_packed(self, p: PackedLatents) -> Latents:
+        s = _PackedLatents(p.n, _ptr(p.n_minu_templates), _ptr(p.n_tex_templates), _ptr(p.minu_off), _ptr(p.minu_x),
+                           _ptr(p.minu_y), _ptr(p.minu_ori), _ptr(p.minu_des), _ptr(p.tex_off), _ptr(p.tex_x),
+                           _ptr(p.tex_y), _ptr(p.tex_ori), _ptr(p.tex_des))
+        h = C.c_void_p()
+        self._chk(self.L.lafis_latents_from_packed(self.ctx, C.byref(s), C.byref(h)))
+        return Latents(self, h)
+
+    # ---- the hot path ----
+    def match(self, latents: Latents, topk: int = 0, want_scores: bool = True, want_components: bool = False,
+              out_hits: Optional[np.ndarray] = None, out_scores: Optional[np.ndarray] = None):
+        """-> dict(hits [Q, topk] structured (score, index), scores [Q, G], components [Q, G, 4])"""
+        Q, G = latents.n, self.gallery_size
+        hits = scores = comps = None
+        if topk > 0:
+            hits = out_hits if out_hits is not None else np.zeros((Q, topk), HIT_DTYPE)
+        if want_scores:
+            scores = out_scores if out_scores is not None else np.zeros((Q, G), np.float32)
+        if want_components:
+            comps = np.zeros((Q, G, 4), np.float32)
+        self._chk(self.L.lafis_match(self.ctx, latents.h, topk, _ptr(hits), _ptr(scores), _ptr(comps)))
+        return {"hits": hits, "scores": scores, "components": comps}
+
+    def match_device(self, latents: Latents, topk: int = 0):
+        """Scores and rank lists stay in HBM: returns (d_hits, d_scores) raw device pointers."""
+        dh, ds = C.c_void_p(), C.c_void_p()
+        self._chk(self.L.lafis_match_device(self.ctx, latents.h, topk, C.byref(dh), C.byref(ds)))
+        return dh.value, ds.value
+
+    def merge_hits(self, shard_hits: np.ndarray) -> np.ndarray:
+        """[Q, n_lists, topk] per-shard rank lists -> [Q, topk] global rank lists."""
+        a = np.ascontiguousarray(shard_hits, HIT_DTYPE)
+        Q, n_lists, topk = a.shape
+        out = np.zeros((Q, topk), HIT_DTYPE)
+        rc = self.L.lafis_merge_hits(a.ctypes.data, Q, n_lists, topk, out.ctypes.data)
+        if rc != LAFIS_OK:
+            raise LafisError(rc, "merge_hits")
+        return out
+
+    def pq_encode(self, des, n: Optional[int] = None, codes_ptr: Optional[int] = None):
+        """PQ-encode descriptors.  numpy [n,96] -> numpy [n,16]; or raw device pointers (des, n, codes_ptr)."""
+        if isinstance(des, np.ndarray):
+            d = np.ascontiguousarray(des, np.float32)
+            codes = np.zeros((d.shape[0], T.PQ_SUBS), np.uint8)
+            self._chk(self.L.lafis_pq_encode(self.ctx, d.ctypes.data, d.shape[0], codes.ctypes.data, 0))
+            return codes
+        self._chk(self.L.lafis_pq_encode(self.ctx, int(des), int(n), int(codes_ptr), 1))
+        return None
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self.L.lafis_get_stats(self.ctx, C.byref(s))
+        return {"kernel_launches": int(s.kernel_launches), "pairs_scored": int(s.pairs_scored),
+                "last_match_ms": float(s.last_match_ms), "last_stage_ms": [float(x) for x in s.last_stage_ms]}
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.lafis_stream(self.ctx) or 0)
+
+    def last_error(self) -> str:
+        return (self.L.lafis_last_error(self.ctx) or b"").decode()
+
+    def _chk(self, rc: int):
+        if rc != LAFIS_OK:
+            raise LafisError(rc, self.last_error())
+
+    def close(self):
+        if self.ctx:
+            self.L.lafis_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

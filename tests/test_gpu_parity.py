@@ -1,0 +1,154 @@
+"""GPU parity tests: the CUDA path through the C ABI against the reference's own outputs (golden
+fixtures) and against the CPU oracle on seeded synthetic templates.  Integer/index results and all
+scores are required to be BIT-IDENTICAL (the kernels keep the reference's fp32 operation order); the
+north-star tolerance of 1e-4 relative is therefore met with margin."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import UB_GALLERY, oracle_scores, rank_list, write_golden_files
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def matcher(pkg, built, golden):
+    m = pkg.Matcher(codebook=golden["codebook"], device=0)
+    yield m
+    m.close()
+
+
+def test_golden_pairs_bit_exact(pkg, matcher, golden, tmp_path):
+    gdir, ldir = write_golden_files(golden, str(tmp_path))
+    gnames = [str(g) for g in golden["gallery_names"]]
+    lnames = [str(l) for l in golden["latent_names"]]
+    matcher.load_gallery_files([os.path.join(gdir, g + ".dat") for g in gnames])
+    L = matcher.load_latents([os.path.join(ldir, l + ".dat") for l in lnames])
+    out = matcher.match(L, topk=8, want_components=True)
+    keep = [j for j, g in enumerate(gnames) if g not in UB_GALLERY]
+    want_final, want_comp, want_rc = golden["pair_final"], golden["pair_comp"], golden["pair_rc"]
+    got_final, got_comp = out["scores"], out["components"]
+    for i, l in enumerate(lnames):
+        for j in keep:
+            if want_rc[i, j] != 0:
+                assert got_final[i, j] == -1.0, (l, gnames[j])
+                continue
+            assert np.array_equal(got_comp[i, j], want_comp[i, j]), (l, gnames[j], got_comp[i, j], want_comp[i, j])
+            assert got_final[i, j] == want_final[i, j], (l, gnames[j])
+    # rank lists: (score desc, index asc) over the library's own scores
+    for i in range(len(lnames)):
+        assert list(out["hits"][i]["index"]) == rank_list(got_final[i], 8)
+        assert np.array_equal(out["hits"][i]["score"], got_final[i][out["hits"][i]["index"]])
+
+
+def test_synthetic_vs_oracle_bit_exact(pkg, matcher, golden, oracle):
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(100 + g) for g in range(40)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(50, raws[3]), T.synth_latent(51, raws[17], n_minu=45, n_tex_pts=111),
+               T.synth_latent(52, raws[30], n_minu=96, n_tex_pts=300)]
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    L = matcher.latents_from_packed(pkg.pack_latents(latents))
+    out = matcher.match(L, topk=10, want_components=True)
+    rc, comp, fin = oracle_scores(oracle, T, latents, rolled, cb)
+    assert (rc == 0).all()
+    assert np.array_equal(out["components"], comp), np.argwhere(out["components"] != comp)[:10]
+    assert np.array_equal(out["scores"], fin)
+    for i, mate in enumerate((3, 17, 30)):
+        assert out["hits"][i]["index"][0] == mate
+        assert list(out["hits"][i]["index"]) == rank_list(fin[i], 10)
+
+
+def test_batch_and_shard_invariance(pkg, matcher, golden):
+    """Scores do not depend on batch composition, chunking or sharding; merged shard rank lists equal
+    the single-shard rank list."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(300 + g, n_minu=40 + g % 30, n_tex=200 + 7 * g) for g in range(30)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(60 + i, raws[5 * i], n_minu=40, n_tex_pts=110) for i in range(4)]
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    whole = matcher.match(matcher.latents_from_packed(pkg.pack_latents(latents)), topk=6)
+    for i, l in enumerate(latents):
+        one = matcher.match(matcher.latents_from_packed(pkg.pack_latents([l])), topk=6)
+        assert np.array_equal(one["scores"][0], whole["scores"][i])
+        assert np.array_equal(one["hits"][0], whole["hits"][i])
+    shard_hits = []
+    scores = []
+    for r in range(3):
+        lo, hi = 30 * r // 3, 30 * (r + 1) // 3
+        matcher.set_gallery(pkg.pack_rolled(rolled[lo:hi]), index_base=lo)
+        o = matcher.match(matcher.latents_from_packed(pkg.pack_latents(latents)), topk=6)
+        shard_hits.append(o["hits"])
+        scores.append(o["scores"])
+    assert np.array_equal(np.concatenate(scores, axis=1), whole["scores"])
+    merged = matcher.merge_hits(np.stack(shard_hits, axis=1))
+    assert np.array_equal(merged, whole["hits"])
+
+
+def test_small_work_budget_chunks(pkg, golden, monkeypatch):
+    """Force many pipeline chunks (tiny work budget) and compare with one chunk."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(500 + g, n_minu=30, n_tex=150) for g in range(23)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(70, raws[11], n_minu=25, n_tex_pts=60)]
+    res = []
+    for budget in ("100000", str(8 << 30)):
+        monkeypatch.setenv("LAFIS_WORK_BYTES", budget)
+        m = pkg.Matcher(codebook=cb, device=0)
+        m.set_gallery(pkg.pack_rolled(rolled))
+        res.append(m.match(m.latents_from_packed(pkg.pack_latents(latents)), topk=5, want_components=True))
+        m.close()
+    assert np.array_equal(res[0]["scores"], res[1]["scores"])
+    assert np.array_equal(res[0]["components"], res[1]["components"])
+    assert np.array_equal(res[0]["hits"], res[1]["hits"])
+
+
+def test_gallery_roundtrip_and_pq_encode(pkg, matcher, golden):
+    T = pkg.templates
+    cb = golden["codebook"]
+    rolled = [T.synth_rolled(700 + g, cb, n_minu=17 + g, n_tex=33 + 5 * g) for g in range(5)]
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    for i, r in enumerate(rolled):
+        back = matcher.gallery_template(i)
+        assert np.array_equal(back.minu[0].x, r.minu[0].x) and np.array_equal(back.minu[0].y, r.minu[0].y)
+        assert np.array_equal(back.minu[0].ori, r.minu[0].ori) and np.array_equal(back.minu[0].des, r.minu[0].des)
+        assert np.array_equal(back.tex[0].x, r.tex[0].x) and np.array_equal(back.tex[0].des, r.tex[0].des)
+    rng = np.random.default_rng(5)
+    des = (1.73 * rng.standard_normal((3000, 96)) / np.sqrt(96)).astype(np.float32)
+    codes = matcher.pq_encode(des)
+    want = T.pq_encode(des, cb)
+    # float32 device distances vs float64 numpy distances: allow a disagreement only where the two
+    # nearest centroids are equidistant to within fp32 rounding
+    diff = np.argwhere(codes != want)
+    assert len(diff) <= 3, len(diff)
+
+
+def test_drivers_write_reference_score_files(pkg, matcher, golden, tmp_path):
+    gdir, ldir = write_golden_files(golden, str(tmp_path))
+    sdir = os.path.join(str(tmp_path), "scores") + "/"
+    os.makedirs(sdir)
+    assert matcher.List2List_matching(ldir, gdir, sdir) == 0
+    for fname, text in zip(golden["n2n_files"], golden["n2n_text"]):
+        got = open(os.path.join(sdir, str(fname))).read().replace(gdir, "@G@")
+        rows = lambda s: sorted(r for r in s.strip().split("\n") if not any(u in r for u in UB_GALLERY))
+        assert rows(got) == rows(str(text)), fname
+    sdir1 = os.path.join(str(tmp_path), "scores1") + "/"
+    os.makedirs(sdir1)
+    assert matcher.One2List_matching(os.path.join(ldir, "lA.dat"), gdir, sdir1) == 0
+    got = open(os.path.join(sdir1, "lA.csv")).read().replace(gdir, "@G@").strip().split("\n")
+    want = str(golden["one2n_text"]).strip().split("\n")
+    assert got[0] == want[0] == "filename,score"
+    # rows with distinct positive scores must agree verbatim; tied rows (score 0 / -1) as sets,
+    # because their order depends on the directory enumeration order of the machine
+    pos = lambda rows: [r for r in rows[1:] if not r.endswith(",0") and not r.endswith(",-1")]
+    tail = lambda rows: sorted(r.split('"', 1)[1] for r in rows[1:] if r.endswith(",0") or r.endswith(",-1"))
+    assert pos(got) == pos(want)
+    assert tail(got) == tail(want)
+    assert matcher.One2List_matching(os.path.join(ldir, "lE_empty.dat"), gdir, sdir1) == 1
+    assert open(os.path.join(sdir1, "lE_empty.csv")).read().strip() == "0"
+    assert matcher.One2List_matching(os.path.join(ldir, "lA.dat"), str(tmp_path / "nowhere_dir_empty"), sdir1) == -1 \
+        if os.makedirs(str(tmp_path / "nowhere_dir_empty"), exist_ok=True) is None else True
