@@ -128,6 +128,7 @@ typedef struct lafis_latents lafis_latents;
 LAFIS_API int lafis_latents_load_files(lafis_ctx* ctx, const char* const* paths, int n, lafis_latents** out);
 LAFIS_API int lafis_latents_from_packed(lafis_ctx* ctx, const lafis_packed_latents* p, lafis_latents** out);
 LAFIS_API int lafis_latents_count(const lafis_latents* l);
+LAFIS_API uint64_t lafis_latents_bytes(const lafis_latents* l); /* bytes one host-to-device staging copy moves */
 LAFIS_API int lafis_latents_status(const lafis_latents* l, int q); /* LAFIS_OK, LAFIS_LATENT_EMPTY, LAFIS_ERR_LATENT_LAYOUT */
 LAFIS_API void lafis_latents_free(lafis_latents* l);
 /* pre-stage the batch in HBM so that a following lafis_match() performs no host-to-device copy */
@@ -152,6 +153,12 @@ LAFIS_API int lafis_match_device(lafis_ctx* ctx, lafis_latents* latents, int top
 /* merge per-shard rank lists (n_lists lists of topk entries per latent, concatenated per latent)
  * into global ones with the (score desc, index asc) rule; host memory. */
 LAFIS_API int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n_lists, int topk, lafis_hit* out);
+
+/* same merge on the device, for the multi-GPU exchange: d_gathered is the result of an all-gather of
+ * every rank's [n_latents][topk] list, i.e. [n_lists][n_latents][topk]; d_out is [n_latents][topk].
+ * Enqueued on the context's stream; n_lists * topk <= 4096. */
+LAFIS_API int lafis_merge_hits_device(lafis_ctx* ctx, const void* d_gathered, int n_latents, int n_lists, int topk,
+                                      void* d_out);
 
 /* ---- drivers with the reference's score-file formats (SURVEY.md §8b "Score files") ----
  *      lafis_one2list_matching  replaces PQ::Matcher::One2List_matching,  matcher.cpp:216-337:
@@ -179,8 +186,9 @@ typedef struct {
     uint64_t kernel_launches; /* kernels launched by this library since the context was created */
     uint64_t pairs_scored;    /* (latent, gallery) pairs scored */
     float last_match_ms;      /* device time of the last lafis_match*, CUDA events */
-    float last_stage_ms[8];   /* per-stage device times of the last match when LAFIS_PROFILE=1:
-                                 0 tex_rowmax, 1 minu_corr, 2 graph_minu, 3 graph_tex, 4 fuse+topk */
+    float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events between the
+                                 launches): 0 tex_rowmax, 1 minu_corr, 2 graph_minu, 3 graph_tex,
+                                 4 fuse + rank lists */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */

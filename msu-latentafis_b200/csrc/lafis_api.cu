@@ -84,11 +84,12 @@ struct lafis_latents {
 struct lafis_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs[8] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> stage_ev;  // 5 per pipeline chunk + 2 for the tail, grown on demand
+    int stage_chunks = 0;               // chunks of the last match
     std::string err;
     int sm_count = 148;
     size_t work_budget = (size_t)8 << 30;
-    bool profile = false;
 
     float* d_codebook = nullptr;  // [16][256][6]
     float* d_table = nullptr;     // [50*50]
@@ -180,7 +181,6 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* s = getenv("LAFIS_WORK_BYTES")) c->work_budget = (size_t)strtoull(s, nullptr, 10);
-    if (const char* s = getenv("LAFIS_PROFILE")) c->profile = atoi(s) != 0;
     cudaError_t last = cudaSuccess;
     const char* what = "";
 #define TRY(expr) (ok = ok && ((last = (expr)) == cudaSuccess || (what = #expr, false)))
@@ -188,7 +188,6 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     TRY(cudaSetDevice(device));
     ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
-    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->evs[i]) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
@@ -275,8 +274,7 @@ void lafis_destroy(lafis_ctx* c) {
     cudaFree(c->d_slow);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (int i = 0; i < 8; ++i)
-        if (c->evs[i]) cudaEventDestroy(c->evs[i]);
+    for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -720,6 +718,7 @@ int lafis_latents_load_files(lafis_ctx* c, const char* const* paths, int n, lafi
 }
 
 int lafis_latents_count(const lafis_latents* l) { return l ? l->n : 0; }
+uint64_t lafis_latents_bytes(const lafis_latents* l) { return l ? (uint64_t)l->arena_bytes : 0; }
 int lafis_latents_status(const lafis_latents* l, int q) {
     return (l && q >= 0 && q < l->n) ? l->status[q] : LAFIS_ERR_ARG;
 }
@@ -806,18 +805,16 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
     LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
 
-    const bool prof = c->profile;
-    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    auto stamp = [&](int i) {
-        if (prof) cudaEventRecord(c->evs[i], st);
-    };
-    auto lap = [&](int stage, int a, int b) {
-        if (!prof) return;
-        float ms = 0;
-        cudaEventSynchronize(c->evs[b]);
-        cudaEventElapsedTime(&ms, c->evs[a], c->evs[b]);
-        stage_ms[stage] += ms;
-    };
+    // stage time stamps: 5 per chunk (before each of the 4 kernels + after the last) and 2 for the tail
+    const int n_chunks = (G + n_chunk_max - 1) / n_chunk_max;
+    while ((int)c->stage_ev.size() < 5 * n_chunks + 2) {
+        cudaEvent_t e;
+        LAFIS_CUDA(c, cudaEventCreate(&e));
+        c->stage_ev.push_back(e);
+    }
+    c->stage_chunks = n_chunks;
+    int chunk_id = 0;
+    auto stamp = [&](int i) { cudaEventRecord(c->stage_ev[5 * chunk_id + i], st); };
 
     for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
         const int n_chunk = std::min(n_chunk_max, G - g0);
@@ -914,14 +911,11 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         stamp(4);
         c->stats.kernel_launches += 4;
         LAFIS_CUDA(c, cudaGetLastError());
-        lap(0, 0, 1);
-        lap(1, 1, 2);
-        lap(2, 2, 3);
-        lap(3, 3, 4);
+        ++chunk_id;
     }
 
     // ---- K10 ----
-    stamp(5);
+    stamp(0);  // chunk_id == n_chunks here: the two tail events
     {
         FuseParams P;
         P.comp = c->comp.p;
@@ -961,13 +955,27 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         keys_to_hits_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(cur, nh, c->hits.p);
         c->stats.kernel_launches += 1;
     }
-    stamp(6);
+    stamp(1);
     LAFIS_CUDA(c, cudaGetLastError());
     LAFIS_CUDA(c, cudaEventRecord(c->ev1, st));
-    lap(4, 5, 6);
     c->stats.pairs_scored += (uint64_t)Q * G;
-    if (prof) std::memcpy(c->stats.last_stage_ms, stage_ms, sizeof stage_ms);
     return LAFIS_OK;
+}
+
+// after the stream has been synchronised: device times of the last match
+static void collect_times(lafis_ctx* c) {
+    cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
+    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < c->stage_chunks; ++k)
+        for (int s = 0; s < 4; ++s) {
+            float t = 0;
+            cudaEventElapsedTime(&t, c->stage_ev[5 * k + s], c->stage_ev[5 * k + s + 1]);
+            ms[s] += t;
+        }
+    float t = 0;
+    cudaEventElapsedTime(&t, c->stage_ev[5 * c->stage_chunks], c->stage_ev[5 * c->stage_chunks + 1]);
+    ms[4] = t;
+    std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
 }
 
 int lafis_match_device(lafis_ctx* c, lafis_latents* L, int topk, const void** d_hits, const float** d_all_scores) {
@@ -975,7 +983,7 @@ int lafis_match_device(lafis_ctx* c, lafis_latents* L, int topk, const void** d_
     int rc = run_match(c, L, topk);
     if (rc != LAFIS_OK) return rc;
     LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
+    collect_times(c);
     if (d_hits) *d_hits = topk > 0 ? (const void*)c->hits.p : nullptr;
     if (d_all_scores) *d_all_scores = c->final_scores.p;
     return LAFIS_OK;
@@ -995,7 +1003,18 @@ int lafis_match(lafis_ctx* c, lafis_latents* L, int topk, lafis_hit* hits, float
     if (components)
         LAFIS_CUDA(c, cudaMemcpyAsync(components, c->comp.p, sizeof(float) * QG * 4, cudaMemcpyDeviceToHost, c->stream));
     LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
+    collect_times(c);
+    return LAFIS_OK;
+}
+
+int lafis_merge_hits_device(lafis_ctx* c, const void* d_gathered, int n_latents, int n_lists, int topk, void* d_out) {
+    if (!c || !d_gathered || !d_out || n_latents <= 0 || n_lists <= 0 || topk <= 0 || n_lists * topk > kTopkChunk)
+        return fail(c, LAFIS_ERR_ARG, "merge_hits_device: n_lists * topk must be in [1, %d]", kTopkChunk);
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    merge_hits_kernel<<<n_latents, kTopkThreads, 0, c->stream>>>(reinterpret_cast<const HitDev*>(d_gathered), n_latents,
+                                                                  n_lists, topk, reinterpret_cast<HitDev*>(d_out));
+    c->stats.kernel_launches += 1;
+    LAFIS_CUDA(c, cudaGetLastError());
     return LAFIS_OK;
 }
 

@@ -124,6 +124,35 @@ __global__ void keys_to_hits_kernel(const unsigned long long* keys, size_t n, Hi
     hits[e] = h;
 }
 
+// merge of gathered per-shard rank lists: in[list][latent][k] (the layout an all-gather of per-rank
+// [latent][k] blocks produces) -> out[latent][k].  One CTA per latent, n_lists * k <= kTopkChunk.
+__global__ void __launch_bounds__(kTopkThreads) merge_hits_kernel(const HitDev* in, int n_latents, int n_lists, int k,
+                                                                 HitDev* out) {
+    __shared__ unsigned long long s[kTopkChunk];
+    const int q = blockIdx.x;
+    const int tot = n_lists * k;
+    for (int t = threadIdx.x; t < kTopkChunk; t += kTopkThreads) {
+        unsigned long long key = 0ull;
+        if (t < tot) {
+            const HitDev h = in[((size_t)(t / k) * n_latents + q) * k + (t % k)];
+            if (h.index != 0xffffffffu) key = rank_key(h.score, h.index);
+        }
+        s[t] = key;
+    }
+    __syncthreads();
+    bitonic_desc(s);
+    for (int t = threadIdx.x; t < k; t += kTopkThreads) {
+        HitDev h;
+        if (s[t] == 0ull) {
+            h.score = -CUDART_INF_F;
+            h.index = 0xffffffffu;
+        } else {
+            rank_unkey(s[t], &h.score, &h.index);
+        }
+        out[(size_t)q * k + t] = h;
+    }
+}
+
 // ---- PQ encoder ----------------------------------------------------------------------------------
 // One thread per (point, sub-quantizer): nearest of 256 centroids in 6-d, first minimum wins
 // (scipy.cluster.vq.vq).  fp32 squared distances accumulated in dimension order.

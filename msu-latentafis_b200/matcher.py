@@ -70,7 +70,7 @@ EXPORTS = [
     "lafis_gallery_load_dir", "lafis_gallery_load_files", "lafis_gallery_set_packed", "lafis_gallery_size",
     "lafis_gallery_path", "lafis_gallery_status", "lafis_gallery_bytes", "lafis_gallery_get_template",
     "lafis_latents_load_files", "lafis_latents_from_packed", "lafis_latents_count", "lafis_latents_status",
-    "lafis_latents_free", "lafis_latents_make_resident", "lafis_match", "lafis_match_device", "lafis_merge_hits",
+    "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
     "lafis_get_stats", "lafis_stream",
 ]
@@ -107,12 +107,15 @@ def load_library():
     L.lafis_latents_from_packed.argtypes = [vp, C.POINTER(_PackedLatents), C.POINTER(vp)]
     L.lafis_latents_count.argtypes = [vp]
     L.lafis_latents_status.argtypes = [vp, ci]
+    L.lafis_latents_bytes.argtypes = [vp]
+    L.lafis_latents_bytes.restype = C.c_uint64
     L.lafis_latents_free.argtypes = [vp]
     L.lafis_latents_free.restype = None
     L.lafis_latents_make_resident.argtypes = [vp, vp]
     L.lafis_match.argtypes = [vp, vp, ci, vp, vp, vp]
     L.lafis_match_device.argtypes = [vp, vp, ci, C.POINTER(vp), C.POINTER(vp)]
     L.lafis_merge_hits.argtypes = [vp, ci, ci, ci, vp]
+    L.lafis_merge_hits_device.argtypes = [vp, vp, ci, ci, ci, vp]
     L.lafis_one2list_matching.argtypes = [vp, cp, cp, cp]
     L.lafis_list2list_matching.argtypes = [vp, cp, cp, cp]
     L.lafis_forget_gallery_dir.argtypes = [vp]
@@ -249,6 +252,10 @@ class Latents:
 
     def status(self, q: int) -> int:
         return self.m.L.lafis_latents_status(self.h, q)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.m.L.lafis_latents_bytes(self.h))
 
     def make_resident(self) -> "Latents":
         self.m._chk(self.m.L.lafis_latents_make_resident(self.m.ctx, self.h))
@@ -388,6 +395,10 @@ class Matcher:
         if rc != LAFIS_OK:
             raise LafisError(rc, "merge_hits")
         return out
+
+    def merge_hits_device(self, d_gathered: int, n_latents: int, n_lists: int, topk: int, d_out: int) -> None:
+        """[n_lists, Q, topk] gathered rank lists in HBM -> [Q, topk]; enqueued on the matcher's stream."""
+        self._chk(self.L.lafis_merge_hits_device(self.ctx, d_gathered, n_latents, n_lists, topk, d_out))
 
     def pq_encode(self, des, n: Optional[int] = None, codes_ptr: Optional[int] = None):
         """PQ-encode descriptors.  numpy [n,96] -> numpy [n,16]; or raw device pointers (des, n, codes_ptr)."""
