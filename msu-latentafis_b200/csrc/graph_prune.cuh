@@ -7,7 +7,8 @@
 //              LSS_R_Fast2 + adjust_angle           matching/matcher.cpp:1471-1647 (K9, both)
 //              score = sum of surviving similarities :508-514, :775-781            (K9b)
 //
-// One CTA per (latent, gallery template, component).  All intermediate state lives in shared
+// DENSE variant (fallback for jobs the sparse fast path of graph_sparse.cuh cannot hold: mated pairs,
+// whose consistency graphs are dense).  One CTA per job.  All intermediate state lives in shared
 // memory: the pairwise compatibility matrix H (fp32 for the distance graph, bytes for the angle
 // graph), the power-iteration vectors and the candidate lists.  Every floating-point step uses the
 // reference's operation order with unfused fp32 / genuine fp64 where the reference's literals force
@@ -269,34 +270,40 @@ struct GraphMinuParams {
 constexpr int kGraphMinuThreads = 128;
 constexpr size_t kGraphMinuSmem = sizeof(float) * kTopCorrMinu * kTopCorrMinu + sizeof(GraphWork<kTopCorrMinu>);
 
-__global__ void __launch_bounds__(kGraphMinuThreads) graph_minu_kernel(GraphMinuParams P) {
+// Dense fallback: processes the jobs the sparse kernel (graph_sparse.cuh) could not hold.
+__global__ void __launch_bounds__(kGraphMinuThreads) graph_minu_dense_kernel(GraphMinuParams P, const int* job_count,
+                                                                             const int* jobs) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* H = reinterpret_cast<float*>(smem);
     GraphWork<kTopCorrMinu>& w = *reinterpret_cast<GraphWork<kTopCorrMinu>*>(smem + sizeof(float) * kTopCorrMinu * kTopCorrMinu);
     const int tid = threadIdx.x;
-    const size_t oidx = blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
-    const int slot = (int)(oidx % 3);
-    const size_t pair = oidx / 3;
-    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
-    const int num = P.corr_n[oidx];
-    if (num > 0 && tid < num) {
-        const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
-        const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
-        w.v[tid] = P.corr_v[oidx * kTopCorrMinu + tid];
-        w.li[tid] = i;
-        w.rj[tid] = j;
-        const uint32_t lo = P.slot_off[q * 3 + slot] + i, go = P.minu_off[P.g0 + tl] + j;
-        const short2 a = P.lat_xy[lo], b = P.gal_xy[go];
-        w.lx[tid] = a.x;
-        w.ly[tid] = a.y;
-        w.rx[tid] = b.x;
-        w.ry[tid] = b.y;
-        w.lo[tid] = P.lat_ori[lo];
-        w.ro[tid] = P.gal_ori[go];
+    const int n_jobs = *job_count;
+    for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        const size_t oidx = (size_t)jobs[jb];  // (q * n_chunk + tl) * 3 + slot
+        const int slot = (int)(oidx % 3);
+        const size_t pair = oidx / 3;
+        const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+        const int num = P.corr_n[oidx];
+        __syncthreads();  // previous job's shared state no longer in use
+        if (num > 0 && tid < num) {
+            const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
+            const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
+            w.v[tid] = P.corr_v[oidx * kTopCorrMinu + tid];
+            w.li[tid] = i;
+            w.rj[tid] = j;
+            const uint32_t lo = P.slot_off[q * 3 + slot] + i, go = P.minu_off[P.g0 + tl] + j;
+            const short2 a = P.lat_xy[lo], b = P.gal_xy[go];
+            w.lx[tid] = a.x;
+            w.ly[tid] = a.y;
+            w.rx[tid] = b.x;
+            w.ry[tid] = b.y;
+            w.lo[tid] = P.lat_ori[lo];
+            w.ro[tid] = P.gal_ori[go];
+        }
+        __syncthreads();
+        const float score = prune_cascade<kTopCorrMinu, kGraphMinuThreads, false>(w, num, H, nullptr);
+        if (tid == 0) P.comp[((size_t)q * P.G + P.g0 + tl) * 4 + slot] = score;
     }
-    __syncthreads();
-    const float score = prune_cascade<kTopCorrMinu, kGraphMinuThreads, false>(w, num, H, nullptr);
-    if (tid == 0) P.comp[((size_t)q * P.G + P.g0 + tl) * 4 + slot] = score;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,78 +339,83 @@ struct TexRowWork {
 constexpr size_t kGraphTexSmem =
     sizeof(float) * kTopCorrTex * kTopCorrTex + sizeof(GraphWork<kTopCorrTex>) + sizeof(TexRowWork);
 
-__global__ void __launch_bounds__(kGraphTexThreads) graph_tex_kernel(GraphTexParams P) {
+__global__ void __launch_bounds__(kGraphTexThreads) graph_tex_dense_kernel(GraphTexParams P, const int* job_count,
+                                                                           const int* jobs) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* H = reinterpret_cast<float*>(smem);
     GraphWork<kTopCorrTex>& w = *reinterpret_cast<GraphWork<kTopCorrTex>*>(smem + sizeof(float) * kTopCorrTex * kTopCorrTex);
     TexRowWork& r = *reinterpret_cast<TexRowWork*>(smem + sizeof(float) * kTopCorrTex * kTopCorrTex + sizeof(GraphWork<kTopCorrTex>));
     const int tid = threadIdx.x;
-    const size_t pair = blockIdx.x;
-    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
-    const int g = P.g0 + tl;
-    const int nLt = (P.lat_status[q] == 0) ? P.lat_nt[q] : 0;
-    const uint32_t gbase = P.tex_off[g];
-    const int nRt = (int)(P.tex_off[g + 1] - gbase);
-    if (nLt <= 0 || nRt <= 0) {  // matcher.cpp:411: no texture template on one side, score stays 0
-        if (tid == 0) P.comp[((size_t)q * P.G + g) * 4 + 3] = 0.0f;
-        return;
-    }
+    const int n_jobs = *job_count;
     for (int e = tid; e < kTableN * kTableN; e += kGraphTexThreads) r.table[e] = P.table[e];
-    const size_t rbase = pair * (size_t)P.lt_stride;
-    for (int i = tid; i < nLt; i += kGraphTexThreads) {
-        r.rv[i] = P.rowmax_val[rbase + i];
-        r.rj[i] = P.rowmax_j[rbase + i];
-    }
-    if (tid == 0) r.flag = 0;
-    __syncthreads();
-
-    // ---- K3b: the N best rows in std::sort order (matcher.cpp:736-749) ----
-    int num;
-    if (nLt > kTopCorrTex) {
-        for (int i = tid; i < nLt; i += kGraphTexThreads) {
-            const float mk = r.rv[i];
-            int rank = 0;
-            bool tie = false;
-            for (int k = 0; k < nLt; ++k) {
-                const float ok = r.rv[k];
-                rank += (ok > mk) || (ok == mk && k < i);
-                tie |= (ok == mk && k != i);
-            }
-            r.ry[rank] = i;
-            // a tie group matters when it reaches into the first N positions
-            if (tie && rank <= kTopCorrTex) r.flag = 1;
+    for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        const size_t pair = (size_t)jobs[jb];
+        const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+        const int g = P.g0 + tl;
+        const int nLt = (P.lat_status[q] == 0) ? P.lat_nt[q] : 0;
+        const uint32_t gbase = P.tex_off[g];
+        const int nRt = (int)(P.tex_off[g + 1] - gbase);
+        __syncthreads();  // previous job's shared state no longer in use
+        if (nLt <= 0 || nRt <= 0) {  // matcher.cpp:411: no texture template on one side, score stays 0
+            if (tid == 0) P.comp[((size_t)q * P.G + g) * 4 + 3] = 0.0f;
+            continue;
         }
+        const size_t rbase = pair * (size_t)P.lt_stride;
+        for (int i = tid; i < nLt; i += kGraphTexThreads) {
+            r.rv[i] = P.rowmax_val[rbase + i];
+            r.rj[i] = P.rowmax_j[rbase + i];
+        }
+        if (tid == 0) r.flag = 0;
         __syncthreads();
-        if (r.flag) {
-            if (tid == 0) {
-                std_sort_desc_prefix(DenseKey<float>{r.rv}, r.ry, nLt, kTopCorrTex);
-                atomicAdd(P.slow_path_count, 1ull);
+
+        // ---- K3b: the N best rows in std::sort order (matcher.cpp:736-749) ----
+        int num;
+        if (nLt > kTopCorrTex) {
+            for (int i = tid; i < nLt; i += kGraphTexThreads) {
+                const float mk = r.rv[i];
+                int rank = 0;
+                bool tie = false;
+                for (int k = 0; k < nLt; ++k) {
+                    const float ok = r.rv[k];
+                    rank += (ok > mk) || (ok == mk && k < i);
+                    tie |= (ok == mk && k != i);
+                }
+                r.ry[rank] = i;
+                // a tie group matters when it reaches into the first N positions
+                if (tie && rank <= kTopCorrTex) r.flag = 1;
             }
             __syncthreads();
+            if (r.flag) {
+                if (tid == 0) {
+                    std_sort_desc_prefix(DenseKey<float>{r.rv}, r.ry, nLt, kTopCorrTex);
+                    atomicAdd(P.slow_path_count, 1ull);
+                }
+                __syncthreads();
+            }
+            num = kTopCorrTex;
+        } else {
+            for (int i = tid; i < nLt; i += kGraphTexThreads) r.ry[i] = i;
+            __syncthreads();
+            num = nLt;
         }
-        num = kTopCorrTex;
-    } else {
-        for (int i = tid; i < nLt; i += kGraphTexThreads) r.ry[i] = i;
+        if (tid < num) {
+            const int i = r.ry[tid];
+            const int j = r.rj[i];
+            w.v[tid] = r.rv[i];
+            w.li[tid] = i;
+            w.rj[tid] = j;
+            const short2 a = P.lat_xy[(size_t)q * P.lt_stride + i], b = P.gal_xy[gbase + j];
+            w.lx[tid] = a.x;
+            w.ly[tid] = a.y;
+            w.rx[tid] = b.x;
+            w.ry[tid] = b.y;
+            w.lo[tid] = P.lat_ori[(size_t)q * P.lt_stride + i];
+            w.ro[tid] = P.gal_ori[gbase + j];
+        }
         __syncthreads();
-        num = nLt;
+        const float score = prune_cascade<kTopCorrTex, kGraphTexThreads, true>(w, num, H, r.table);
+        if (tid == 0) P.comp[((size_t)q * P.G + g) * 4 + 3] = score;
     }
-    if (tid < num) {
-        const int i = r.ry[tid];
-        const int j = r.rj[i];
-        w.v[tid] = r.rv[i];
-        w.li[tid] = i;
-        w.rj[tid] = j;
-        const short2 a = P.lat_xy[(size_t)q * P.lt_stride + i], b = P.gal_xy[gbase + j];
-        w.lx[tid] = a.x;
-        w.ly[tid] = a.y;
-        w.rx[tid] = b.x;
-        w.ry[tid] = b.y;
-        w.lo[tid] = P.lat_ori[(size_t)q * P.lt_stride + i];
-        w.ro[tid] = P.gal_ori[gbase + j];
-    }
-    __syncthreads();
-    const float score = prune_cascade<kTopCorrTex, kGraphTexThreads, true>(w, num, H, r.table);
-    if (tid == 0) P.comp[((size_t)q * P.G + g) * 4 + 3] = score;
 }
 
 }  // namespace lafis

@@ -18,6 +18,7 @@
 #include "dat_format.h"
 #include "device_common.cuh"
 #include "graph_prune.cuh"
+#include "graph_sparse.cuh"
 #include "minu_corr.cuh"
 #include "misc_kernels.cuh"
 #include "tex_rowmax.cuh"
@@ -111,6 +112,8 @@ struct lafis_ctx {
     DevBuf<float> corr_v;
     DevBuf<uint32_t> corr_ij;
     DevBuf<int> corr_n;
+    DevBuf<int> ov_minu, ov_tex;  // overflow job lists of the sparse graph kernels
+    int* d_ov_count = nullptr;    // [2]
     DevBuf<float> comp;
     DevBuf<float> final_scores;
     DevBuf<unsigned long long> keys_a, keys_b;
@@ -191,6 +194,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_ov_count, 2 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_slow, 2 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) {
         // matcher.cpp:49-56: table[i*50+j] = (float)sqrt((16 i)^2 + (16 j)^2), square root in double
@@ -204,8 +208,12 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
         ok = ok && cudaMemset(c->d_slow, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
         TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
         TRY(cudaFuncSetAttribute(minu_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrMaxDynSmem));
-        TRY(cudaFuncSetAttribute(graph_minu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphMinuSmem));
-        TRY(cudaFuncSetAttribute(graph_tex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphTexSmem));
+        TRY(cudaFuncSetAttribute(graph_minu_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphMinuSmem));
+        TRY(cudaFuncSetAttribute(graph_tex_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphTexSmem));
+        TRY(cudaFuncSetAttribute(graph_minu_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SparseWork<false>)));
+        TRY(cudaFuncSetAttribute(graph_tex_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SparseWork<true>)));
     }
 #undef TRY
     if (!ok) {
@@ -262,6 +270,9 @@ void lafis_destroy(lafis_ctx* c) {
     c->corr_v.release();
     c->corr_ij.release();
     c->corr_n.release();
+    c->ov_minu.release();
+    c->ov_tex.release();
+    cudaFree(c->d_ov_count);
     c->comp.release();
     c->final_scores.release();
     c->keys_a.release();
@@ -802,6 +813,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     LAFIS_CUDA(c, c->corr_v.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
     LAFIS_CUDA(c, c->corr_ij.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
     LAFIS_CUDA(c, c->corr_n.reserve((size_t)Q * n_chunk_max * 3));
+    LAFIS_CUDA(c, c->ov_minu.reserve((size_t)Q * n_chunk_max * 3));
+    LAFIS_CUDA(c, c->ov_tex.reserve((size_t)Q * n_chunk_max));
     LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
     LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
 
@@ -883,7 +896,11 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.G = G;
             P.comp = c->comp.p;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
-            graph_minu_kernel<<<grid, kGraphMinuThreads, kGraphMinuSmem, st>>>(P);
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, 2 * sizeof(int), st));
+            graph_minu_sparse_kernel<<<grid, SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
+                P, OverflowList{c->d_ov_count, c->ov_minu.p});
+            graph_minu_dense_kernel<<<std::min<unsigned>(grid, 2u * c->sm_count), kGraphMinuThreads, kGraphMinuSmem, st>>>(
+                P, c->d_ov_count, c->ov_minu.p);
         }
         stamp(3);
         // ---- K3b + K4 + K9 (texture) ----
@@ -906,10 +923,13 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.comp = c->comp.p;
             P.slow_path_count = c->d_slow + 1;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk);
-            graph_tex_kernel<<<grid, kGraphTexThreads, kGraphTexSmem, st>>>(P);
+            graph_tex_sparse_kernel<<<grid, SparseGeom<true>::NT, sizeof(SparseWork<true>), st>>>(
+                P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
+            graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, st>>>(
+                P, c->d_ov_count + 1, c->ov_tex.p);
         }
         stamp(4);
-        c->stats.kernel_launches += 4;
+        c->stats.kernel_launches += 6;
         LAFIS_CUDA(c, cudaGetLastError());
         ++chunk_id;
     }
