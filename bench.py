@@ -311,8 +311,9 @@ def run_b200_arm(args):
     bytes_per_match = gallery_bytes / G  # this shard's 392*nRm + 24*nRt average
     nLt = int(packed.tex_off[1] - packed.tex_off[0])
     # dominant kernel: the one with the largest share of the step
-    names = ["tex_rowmax_kernel", "minu_corr_kernel", "graph_minu_kernel", "graph_tex_kernel", "fuse+topk kernels"]
-    dom = int(np.argmax(stage_ms[:5]))
+    names = ["tex_rowmax_kernel", "minu_sim_kernel", "minu_select_kernel(+slow)", "graph_minu_sparse_kernel(+dense)",
+             "graph_tex_sparse_kernel(+dense)", "fuse+topk kernels"]
+    dom = int(np.argmax(stage_ms[:6]))
     kernel_bytes = kernel_bytes_per_pair(m, G, nLt)
     dom_ms = float(stage_ms[dom])
     achieved = kernel_bytes[dom] * Q * G / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -329,7 +330,7 @@ def run_b200_arm(args):
                         "peak_per_s": smem_peak,
                         "frac": (gathers / (float(stage_ms[0]) / 1e3) / smem_peak) if stage_ms[0] > 0 else 0,
                         "note": "4-byte LUT gathers vs 148 SM x 32 banks x sm_max_mhz; the binding resource (SURVEY.md §8d)"},
-        "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:5])},
+        "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:6])},
     }
 
     cpu = None
@@ -397,10 +398,11 @@ def kernel_bytes_per_pair(m, G, nLt):
     nRm, nRt = nm / n_probe, nt / n_probe
     return {
         0: 16 * nRt + 4 + 6 * nLt,                 # tex_rowmax: PQ codes in, (f32 max, u16 argmax) per latent row out
-        1: 384 * nRm + 6 + 3 * (120 * 8 + 4),      # minu_corr: descriptors in, 3 x top-120 (value, ij) out
-        2: 3 * (120 * 8 + 4) + 8 * nRm + 12,       # graph_minu: candidates + minutiae coordinates in, 3 scores out
-        3: 6 * nLt + 8 * nRt + 4,                  # graph_tex: row maxima + texture coordinates in, 1 score out
-        4: 16 + 4,                                 # fuse: 4 components in, 1 score out
+        1: 384 * nRm + 6 + 3 * 80 * 4 * nRm,       # minu_sim: descriptors in, 3 similarity matrices out
+        2: 3 * 80 * 4 * nRm + 3 * (120 * 8 + 4),   # minu_select: similarity matrices in, 3 x top-120 (value, ij) out
+        3: 3 * (120 * 8 + 4) + 8 * nRm + 12,       # graph_minu: candidates + minutiae coordinates in, 3 scores out
+        4: 6 * nLt + 8 * nRt + 4,                  # graph_tex: row maxima + texture coordinates in, 1 score out
+        5: 16 + 4,                                 # fuse: 4 components in, 1 score out
         "nRm_mean": nRm, "nRt_mean": nRt,
     }
 

@@ -187,8 +187,8 @@ typedef struct {
     uint64_t pairs_scored;    /* (latent, gallery) pairs scored */
     float last_match_ms;      /* device time of the last lafis_match*, CUDA events */
     float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events between the
-                                 launches): 0 tex_rowmax, 1 minu_corr, 2 graph_minu, 3 graph_tex,
-                                 4 fuse + rank lists */
+                                 launches): 0 tex_rowmax, 1 minu_sim, 2 minu_select (+slow), 3 graph_minu
+                                 (sparse + dense), 4 graph_tex (sparse + dense), 5 fuse + rank lists */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */

@@ -19,7 +19,7 @@
 #include "device_common.cuh"
 #include "graph_prune.cuh"
 #include "graph_sparse.cuh"
-#include "minu_corr.cuh"
+#include "minu_sim.cuh"
 #include "misc_kernels.cuh"
 #include "tex_rowmax.cuh"
 
@@ -29,6 +29,8 @@ using namespace lafis;
 // helpers
 // ---------------------------------------------------------------------------------------------------
 namespace {
+
+constexpr int kMaxDynSmem = 227 * 1024 - 1024;  // kernels also hold a little static shared memory
 
 template <typename T>
 struct DevBuf {
@@ -86,11 +88,11 @@ struct lafis_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> stage_ev;  // 5 per pipeline chunk + 2 for the tail, grown on demand
+    std::vector<cudaEvent_t> stage_ev;  // 6 per pipeline chunk + 2 for the tail, grown on demand
     int stage_chunks = 0;               // chunks of the last match
     std::string err;
     int sm_count = 148;
-    size_t work_budget = (size_t)8 << 30;
+    size_t work_budget = (size_t)24 << 30;
 
     float* d_codebook = nullptr;  // [16][256][6]
     float* d_table = nullptr;     // [50*50]
@@ -112,6 +114,9 @@ struct lafis_ctx {
     DevBuf<float> corr_v;
     DevBuf<uint32_t> corr_ij;
     DevBuf<int> corr_n;
+    DevBuf<float> sim;            // S matrices of the current chunk
+    DevBuf<int> slow_jobs;        // selection jobs that need the introsort replay
+    int* d_slow_count = nullptr;
     DevBuf<int> ov_minu, ov_tex;  // overflow job lists of the sparse graph kernels
     int* d_ov_count = nullptr;    // [2]
     DevBuf<float> comp;
@@ -195,6 +200,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_ov_count, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_slow_count, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_slow, 2 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) {
         // matcher.cpp:49-56: table[i*50+j] = (float)sqrt((16 i)^2 + (16 j)^2), square root in double
@@ -207,7 +213,9 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
                               cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemset(c->d_slow, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
         TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
-        TRY(cudaFuncSetAttribute(minu_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrMaxDynSmem));
+        TRY(cudaFuncSetAttribute(minu_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        TRY(cudaFuncSetAttribute(minu_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        TRY(cudaFuncSetAttribute(minu_select_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(graph_minu_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphMinuSmem));
         TRY(cudaFuncSetAttribute(graph_tex_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphTexSmem));
         TRY(cudaFuncSetAttribute(graph_minu_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -270,6 +278,9 @@ void lafis_destroy(lafis_ctx* c) {
     c->corr_v.release();
     c->corr_ij.release();
     c->corr_n.release();
+    c->sim.release();
+    c->slow_jobs.release();
+    cudaFree(c->d_slow_count);
     c->ov_minu.release();
     c->ov_tex.release();
     cudaFree(c->d_ov_count);
@@ -793,14 +804,20 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     D.status = reinterpret_cast<int*>(A + L->o_status);
 
     // ---- geometry ----
-    const int nLs = std::max(32, round_up(L->max_slot_n, 32)), nRs = std::max(32, round_up(c->max_nR, 32));
-    const size_t corr_smem = minu_corr_smem_bytes(nLs, nRs);
-    if (corr_smem > (size_t)kCorrMaxDynSmem || (size_t)nLs * nRs >= 65536)
+    const int maxL = std::max(1, L->max_slot_n), maxLp = (maxL + 3) & ~3;
+    const int maxNp = std::max(4, (c->max_nR + 3) & ~3);
+    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 128;
+    int b_double = 1;
+    if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
+    const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
+    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp), slow_smem = minu_select_slow_smem_bytes(maxL, maxNp);
+    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
         return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE,
-                    "minutiae templates of %d x %d points need %zu bytes of shared memory (limit %d)",
-                    L->max_slot_n, c->max_nR, corr_smem, kCorrMaxDynSmem);
+                    "minutiae templates of %d x %d points need %zu / %zu bytes of shared memory (limit %d)",
+                    L->max_slot_n, c->max_nR, sim_smem, slow_smem, kMaxDynSmem);
+    const size_t job_stride = (size_t)maxL * maxNp;
     const size_t lt = (size_t)L->lt_stride;
-    const size_t per_tpl = (size_t)Q * (lt * 6 + 3 * (kTopCorrMinu * 8 + 4));
+    const size_t per_tpl = (size_t)Q * (lt * 6 + 3 * (kTopCorrMinu * 8 + 4) + 3 * job_stride * 4 + 32);
     size_t chunk_sz = std::max<size_t>(1, c->work_budget / std::max<size_t>(per_tpl, 1));
     chunk_sz = std::min<size_t>(chunk_sz, (size_t)G);
     // keep every grid dimension and flat index comfortably inside 31 bits
@@ -813,21 +830,23 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     LAFIS_CUDA(c, c->corr_v.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
     LAFIS_CUDA(c, c->corr_ij.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
     LAFIS_CUDA(c, c->corr_n.reserve((size_t)Q * n_chunk_max * 3));
+    LAFIS_CUDA(c, c->sim.reserve((size_t)Q * n_chunk_max * 3 * job_stride));
+    LAFIS_CUDA(c, c->slow_jobs.reserve((size_t)Q * n_chunk_max * 3));
     LAFIS_CUDA(c, c->ov_minu.reserve((size_t)Q * n_chunk_max * 3));
     LAFIS_CUDA(c, c->ov_tex.reserve((size_t)Q * n_chunk_max));
     LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
     LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
 
-    // stage time stamps: 5 per chunk (before each of the 4 kernels + after the last) and 2 for the tail
+    // stage time stamps: 6 per chunk (before each of the 5 stages + after the last) and 2 for the tail
     const int n_chunks = (G + n_chunk_max - 1) / n_chunk_max;
-    while ((int)c->stage_ev.size() < 5 * n_chunks + 2) {
+    while ((int)c->stage_ev.size() < 6 * n_chunks + 2) {
         cudaEvent_t e;
         LAFIS_CUDA(c, cudaEventCreate(&e));
         c->stage_ev.push_back(e);
     }
     c->stage_chunks = n_chunks;
     int chunk_id = 0;
-    auto stamp = [&](int i) { cudaEventRecord(c->stage_ev[5 * chunk_id + i], st); };
+    auto stamp = [&](int i) { cudaEventRecord(c->stage_ev[6 * chunk_id + i], st); };
 
     for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
         const int n_chunk = std::min(n_chunk_max, G - g0);
@@ -857,9 +876,9 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, st>>>(P);
         }
         stamp(1);
-        // ---- K5 + K6 + K7 ----
+        // ---- K5, then K6 + K7 ----
         {
-            MinuCorrParams P;
+            MinuSimParams P;
             P.slot_n = D.slot_n;
             P.slot_off = D.slot_off;
             P.lat_desT = D.minu_desT;
@@ -870,15 +889,35 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.minu_desT = c->gal.minu_desT;
             P.g0 = g0;
             P.n_chunk = n_chunk;
-            P.nLs = nLs;
-            P.nRs = nRs;
-            P.corr_v = c->corr_v.p;
-            P.corr_ij = c->corr_ij.p;
-            P.corr_n = c->corr_n.p;
-            P.slow_path_count = c->d_slow;
-            minu_corr_kernel<<<n_chunk, kCorrThreads, corr_smem, st>>>(P);
+            P.a_slot_stride = a_slot_stride;
+            P.b_buf_stride = b_buf_stride;
+            P.b_double = b_double;
+            P.S = c->sim.p;
+            P.job_stride = job_stride;
+            minu_sim_kernel<<<std::min(n_chunk, c->sm_count), kSimThreads, sim_smem, st>>>(P);
+            stamp(2);
+            MinuSelectParams R;
+            R.slot_n = D.slot_n;
+            R.lat_status = D.status;
+            R.Q = Q;
+            R.minu_n = c->gal.minu_n;
+            R.g0 = g0;
+            R.n_chunk = n_chunk;
+            R.S = c->sim.p;
+            R.job_stride = job_stride;
+            R.max_nL = maxL;
+            R.max_np = maxNp;
+            R.corr_v = c->corr_v.p;
+            R.corr_ij = c->corr_ij.p;
+            R.corr_n = c->corr_n.p;
+            R.slow_count = c->d_slow_count;
+            R.slow_jobs = c->slow_jobs.p;
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
+            const unsigned jobs = (unsigned)((size_t)Q * n_chunk * 3);
+            minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
+            minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
         }
-        stamp(2);
+        stamp(3);
         // ---- K8 + K9 (minutiae) ----
         {
             GraphMinuParams P;
@@ -902,7 +941,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             graph_minu_dense_kernel<<<std::min<unsigned>(grid, 2u * c->sm_count), kGraphMinuThreads, kGraphMinuSmem, st>>>(
                 P, c->d_ov_count, c->ov_minu.p);
         }
-        stamp(3);
+        stamp(4);
         // ---- K3b + K4 + K9 (texture) ----
         {
             GraphTexParams P;
@@ -928,8 +967,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, st>>>(
                 P, c->d_ov_count + 1, c->ov_tex.p);
         }
-        stamp(4);
-        c->stats.kernel_launches += 6;
+        stamp(5);
+        c->stats.kernel_launches += 8;
         LAFIS_CUDA(c, cudaGetLastError());
         ++chunk_id;
     }
@@ -987,14 +1026,14 @@ static void collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
     float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < c->stage_chunks; ++k)
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 5; ++s) {
             float t = 0;
-            cudaEventElapsedTime(&t, c->stage_ev[5 * k + s], c->stage_ev[5 * k + s + 1]);
+            cudaEventElapsedTime(&t, c->stage_ev[6 * k + s], c->stage_ev[6 * k + s + 1]);
             ms[s] += t;
         }
     float t = 0;
-    cudaEventElapsedTime(&t, c->stage_ev[5 * c->stage_chunks], c->stage_ev[5 * c->stage_chunks + 1]);
-    ms[4] = t;
+    cudaEventElapsedTime(&t, c->stage_ev[6 * c->stage_chunks], c->stage_ev[6 * c->stage_chunks + 1]);
+    ms[5] = t;
     std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
 }
 

@@ -1,0 +1,463 @@
+// Minutiae-template similarity, normalisation and top-120 candidate selection — stages K5 + K6 + K7,
+// as two kernels (the one-kernel version in minu_corr.cuh spent ~70 % of its time at block barriers).
+//
+//   reference: One2One_minutiae_matching steps 1-3, matching/matcher.cpp:440-488
+//
+// minu_sim_kernel (K5).  Persistent CTAs, one per SM.  S = max(0, A.B^T) for the three selected latent
+// templates of a latent (matcher.cpp:380) against one gallery template per step.  Every output
+// accumulates k = 0..95 in order with an unfused fp32 multiply and add (the Eigen stand-in's order,
+// oracle/shim/Eigen/Dense).  The gallery's k-major descriptor blocks stream through a double buffer
+// with cp.async while the previous block is being multiplied; the latent's blocks stay resident
+// (single latent) or are re-staged per latent (batches).  Warp tile 16 x 128, thread tile 8 x 8: per k
+// four LDS.128 feed 64 multiply-adds.  S goes to HBM ([nL][np] per job) - ~115 KB per pair written once
+// and read once, far below what the path's fp32 issue rate lets HBM see.
+//
+// minu_select_kernel (K6 + K7).  One 256-thread CTA per (latent, template, slot), ~57 KB of shared
+// memory so that three CTAs share an SM and hide each other's barriers.  Column sums (i ascending) and
+// row sums (j ascending) by one thread per column / row over an odd-stride copy of S.  The 120 largest
+// normalised values S/(l_i + r_j - S + 1e-6) are found in two passes over an fp32 estimate of that
+// value (relative error < 1e-6): a 1024-bin histogram of the float bit patterns locates the bin of the
+// 120th value, everything at or above that bin's lower edge (with a 4e-6 relative safety margin, which
+// provably contains the exact top-120) becomes a candidate, and only candidates get the reference's
+// double-precision evaluation (:467).  Candidates are rank-sorted with the total order (value desc,
+// index asc).  If two of the selected values tie, or fewer than 120 values are positive, the
+// permutation libstdc++'s introsort would produce is not implied by the values and the job goes to
+// minu_select_slow_kernel, which evaluates every value in double and replays the introsort
+// (stdsort_emul.h).  The output carries the RAW similarity (:486).
+#pragma once
+#include "device_common.cuh"
+#include "stdsort_emul.h"
+
+namespace lafis {
+
+constexpr int kSimThreads = 512;
+constexpr int kSelThreads = 256;
+constexpr int kSelMaxCand = 512;
+constexpr int kSelBins = 1024;  // float bits >> 20 of values in (0, 1]
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct MinuSimParams {
+    // latent side
+    const int* slot_n;         // [3Q]
+    const uint32_t* slot_off;  // [3Q] padded offsets
+    const float* lat_desT;
+    const int* lat_status;     // [Q]
+    int Q;
+    // gallery side
+    const uint32_t* minu_off;
+    const uint16_t* minu_n;
+    const float* minu_desT;
+    int g0, n_chunk;
+    // shared-memory geometry (floats)
+    int a_slot_stride;  // one latent slot: 96 * max padded slot count + 16
+    int b_buf_stride;   // one gallery block: 96 * max padded template count + 128
+    int b_double;       // two gallery buffers
+    // output: S[job][i * np + j], job = (q * n_chunk + tl) * 3 + slot
+    float* S;
+    size_t job_stride;
+};
+
+__host__ __device__ inline size_t minu_sim_smem_bytes(int a_slot_stride, int b_buf_stride, int b_double) {
+    return sizeof(float) * ((size_t)3 * a_slot_stride + (size_t)(b_double ? 2 : 1) * b_buf_stride);
+}
+
+__global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* A = reinterpret_cast<float*>(smem);        // [3][a_slot_stride]
+    float* B = A + 3 * (size_t)P.a_slot_stride;       // [1|2][b_buf_stride]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSimThreads / 32;
+    const int li = lane >> 4, lj = lane & 15;
+
+    auto load_B = [&](int tl, int buf) {
+        const int g = P.g0 + tl;
+        const int nR = P.minu_n[g];
+        if (nR <= 0) return;
+        const int np = (nR + 3) & ~3;
+        const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * P.minu_off[g]);
+        float4* dst = reinterpret_cast<float4*>(B + (size_t)buf * P.b_buf_stride);
+        for (int e = tid; e < 24 * np; e += kSimThreads) cp_async16(dst + e, src + e);
+    };
+    auto load_A = [&](int q) {
+        for (int s = 0; s < 3; ++s) {
+            const int nL = P.slot_n[q * 3 + s];
+            if (nL <= 0) continue;
+            const int np = (nL + 3) & ~3;
+            const float4* src = reinterpret_cast<const float4*>(P.lat_desT + (size_t)96 * P.slot_off[q * 3 + s]);
+            float4* dst = reinterpret_cast<float4*>(A + (size_t)s * P.a_slot_stride);
+            for (int e = tid; e < 24 * np; e += kSimThreads) cp_async16(dst + e, src + e);
+        }
+    };
+
+    int tl = blockIdx.x;
+    if (tl >= P.n_chunk) return;
+    load_B(tl, 0);
+    if (P.Q == 1) load_A(0);
+    cp_async_commit();
+
+    for (int it = 0; tl < P.n_chunk; tl += gridDim.x, ++it) {
+        const int cur = P.b_double ? (it & 1) : 0;
+        const int tl_next = tl + gridDim.x;
+        bool prefetched = false;
+        if (P.b_double && tl_next < P.n_chunk) {
+            load_B(tl_next, cur ^ 1);
+            prefetched = true;
+        }
+        cp_async_commit();
+        const int g = P.g0 + tl;
+        const int nR = P.minu_n[g];
+        const int npR = (nR + 3) & ~3;
+        const float* Bt = B + (size_t)cur * P.b_buf_stride;
+        const int tiles_j = (nR + 127) >> 7;
+
+        for (int q = 0; q < P.Q; ++q) {
+            const bool live = P.lat_status[q] == 0 && nR > 0;
+            if (P.Q > 1) {
+                __syncthreads();  // previous latent's tiles are done with A
+                if (live) load_A(q);
+                cp_async_commit();
+                cp_async_wait<0>();
+            } else {
+                if (prefetched) cp_async_wait<1>();
+                else cp_async_wait<0>();
+            }
+            __syncthreads();
+            if (!live) continue;
+
+            // tile list over the three slots
+            int t0[4];
+            t0[0] = 0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_j;
+            for (int t = warp; t < t0[3]; t += NW) {
+                const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
+                const int tt = t - t0[s];
+                const int ti = tt / tiles_j, tj = tt - ti * tiles_j;
+                const int nL = P.slot_n[q * 3 + s];
+                const int npL = (nL + 3) & ~3;
+                const int i0 = ti * 16 + li * 8;
+                const int ja = tj * 128 + lj * 4, jb = ja + 64;
+                const float* ap = A + (size_t)s * P.a_slot_stride + i0;
+                const float* bpa = Bt + ja;
+                const float* bpb = Bt + jb;
+                float acc[8][8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+#pragma unroll 2
+                for (int k = 0; k < 96; ++k) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * npL);
+                    const float4 a1 = *reinterpret_cast<const float4*>(ap + k * npL + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) acc[a][b] = f_add(acc[a][b], f_mul(av[a], bv[b]));
+                }
+                float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int i = i0 + a;
+                    if (i >= nL) continue;
+                    float4 v0, v1;
+                    v0.x = acc[a][0] < 0.0f ? 0.0f : acc[a][0];  // matcher.cpp:449-450
+                    v0.y = acc[a][1] < 0.0f ? 0.0f : acc[a][1];
+                    v0.z = acc[a][2] < 0.0f ? 0.0f : acc[a][2];
+                    v0.w = acc[a][3] < 0.0f ? 0.0f : acc[a][3];
+                    v1.x = acc[a][4] < 0.0f ? 0.0f : acc[a][4];
+                    v1.y = acc[a][5] < 0.0f ? 0.0f : acc[a][5];
+                    v1.z = acc[a][6] < 0.0f ? 0.0f : acc[a][6];
+                    v1.w = acc[a][7] < 0.0f ? 0.0f : acc[a][7];
+                    if (ja < npR) *reinterpret_cast<float4*>(out + (size_t)i * npR + ja) = v0;
+                    if (jb < npR) *reinterpret_cast<float4*>(out + (size_t)i * npR + jb) = v1;
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this gallery block before it is overwritten
+        if (!P.b_double && tl_next < P.n_chunk) {
+            load_B(tl_next, 0);
+            cp_async_commit();
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MinuSelectParams {
+    const int* slot_n;
+    const int* lat_status;
+    int Q;
+    const uint16_t* minu_n;
+    int g0, n_chunk;
+    const float* S;
+    size_t job_stride;
+    int max_nL, max_np;  // shared-memory geometry
+    float* corr_v;       // [job][120]
+    uint32_t* corr_ij;   // [job][120] (i << 16) | j
+    int* corr_n;         // [job]
+    int* slow_count;
+    int* slow_jobs;
+};
+
+__host__ __device__ inline size_t minu_select_smem_bytes(int max_nL, int max_np) {
+    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(int) * kSelBins +
+           (sizeof(uint32_t) + sizeof(int)) * kSelMaxCand + 16;
+}
+
+// the reference's normalised similarity, matcher.cpp:467: float sums, "+0.000001" promotes the
+// denominator and the division to double, the quotient is narrowed to float
+__device__ __forceinline__ uint32_t exact_key(float s, float l, float r) {
+    const float den = f_sub(f_add(l, r), s);
+    const double qd = (double)s / ((double)den + 0.000001);
+    uint32_t key = __float_as_uint((float)qd);
+    if (key == 0x80000000u) key = 0;
+    return key;
+}
+// fp32 estimate of the same value; relative error < 1e-6
+__device__ __forceinline__ float approx_key(float s, float l, float r) {
+    const float den = f_sub(f_add(l, r), s);
+    return __fdividef(s, den + 0.000001f);
+}
+
+__global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSelThreads / 32;
+    const size_t job = blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
+    const int slot = (int)(job % 3);
+    const size_t pair = job / 3;
+    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+    const int nR = P.minu_n[P.g0 + tl];
+    const int nL = (P.lat_status[q] == 0) ? P.slot_n[q * 3 + slot] : 0;
+    if (nL <= 0 || nR <= 0) {  // rolled without minutiae / latent slot absent: score stays 0
+        if (tid == 0) P.corr_n[job] = 0;
+        return;
+    }
+    const int np = (nR + 3) & ~3, ld = np + 1;
+    float* Ssm = reinterpret_cast<float*>(smem);                       // [nL][ld]
+    float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);             // [nL]
+    float* rsum = lsum + P.max_nL;                                     // [nR]
+    int* hist = reinterpret_cast<int*>(rsum + P.max_np);               // [1024]
+    uint32_t* cand_key = reinterpret_cast<uint32_t*>(hist + kSelBins); // [512]
+    int* cand_e = reinterpret_cast<int*>(cand_key + kSelMaxCand);      // [512]
+    __shared__ int s_ncand, s_npos, s_flag, s_bin;
+    __shared__ float s_thr;
+    __shared__ int s_order[kTopCorrMinu];
+
+    const float* Sg = P.S + job * P.job_stride;
+    for (int i = warp; i < nL; i += NW)
+        for (int j = lane; j < nR; j += 32) Ssm[i * ld + j] = Sg[(size_t)i * np + j];
+    for (int b = tid; b < kSelBins; b += kSelThreads) hist[b] = 0;
+    if (tid == 0) {
+        s_ncand = 0;
+        s_npos = 0;
+        s_flag = 0;
+    }
+    __syncthreads();
+
+    // ---- K6: sums.  first half of the CTA: columns (i ascending); second half: rows (j ascending) ----
+    if (tid < kSelThreads / 2) {
+        for (int j = tid; j < nR; j += kSelThreads / 2) {
+            float acc = Ssm[j];
+#pragma unroll 8
+            for (int i = 1; i < nL; ++i) acc = f_add(acc, Ssm[i * ld + j]);
+            rsum[j] = acc;
+        }
+    } else {
+        for (int i = tid - kSelThreads / 2; i < nL; i += kSelThreads / 2) {
+            const float* row = Ssm + i * ld;
+            float acc = row[0];
+#pragma unroll 8
+            for (int j = 1; j < nR; ++j) acc = f_add(acc, row[j]);
+            lsum[i] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 1: histogram of the estimates ----
+    const int M = nL * nR;
+    const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
+    {
+        int npos = 0;
+        for (int i = warp; i < nL; i += NW) {
+            const float l = lsum[i];
+            for (int j = lane; j < nR; j += 32) {
+                const float s = Ssm[i * ld + j];
+                if (s > 0.0f) {
+                    const uint32_t bits = __float_as_uint(approx_key(s, l, rsum[j]));
+                    atomicAdd(&hist[min(bits >> 20, (uint32_t)(kSelBins - 1))], 1);
+                    ++npos;
+                }
+            }
+        }
+        npos = __reduce_add_sync(0xffffffffu, npos);
+        if (lane == 0) atomicAdd(&s_npos, npos);
+    }
+    __syncthreads();
+    if (s_npos < K) {  // the 120th value is a zero: ties among zeros decide the order
+        if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
+        return;
+    }
+    if (warp == 0) {  // bin of the K-th largest estimate, scanning 32-bin chunks from the top
+        int above = 0, bin = 0;
+        for (int c = kSelBins / 32 - 1; c >= 0; --c) {
+            const int h = hist[c * 32 + lane];
+            const int tot = __reduce_add_sync(0xffffffffu, h);
+            if (above + tot >= K) {
+                // suffix sums inside the chunk: lanes above me
+                int suf = h;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_down_sync(0xffffffffu, suf, d);
+                    if (lane + d < 32) suf += o;
+                }
+                const bool mine = above + (suf - h) < K && K <= above + suf;
+                const unsigned ball = __ballot_sync(0xffffffffu, mine);
+                bin = c * 32 + (31 - __clz(ball));
+                break;
+            }
+            above += tot;
+        }
+        if (lane == 0) {
+            s_bin = bin;
+            // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side)
+            s_thr = __uint_as_float((uint32_t)bin << 20) * (1.0f - 4e-6f);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: candidates, with the reference's double-precision value ----
+    {
+        const float thr = s_thr;
+        for (int i = warp; i < nL; i += NW) {
+            const float l = lsum[i];
+            for (int j = lane; j < nR; j += 32) {
+                const float s = Ssm[i * ld + j];
+                if (s > 0.0f && approx_key(s, l, rsum[j]) >= thr) {
+                    const int pos = atomicAdd(&s_ncand, 1);
+                    if (pos < kSelMaxCand) {
+                        cand_key[pos] = exact_key(s, l, rsum[j]);
+                        cand_e[pos] = i * nR + j;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nc = s_ncand;
+    if (nc > kSelMaxCand) {  // pathological value distribution: let the slow kernel sort everything
+        if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
+        return;
+    }
+    // ---- K7: rank sort with the total order (value desc, index asc) ----
+    for (int c = tid; c < nc; c += kSelThreads) {
+        const uint32_t mk = cand_key[c];
+        const int me = cand_e[c];
+        int rank = 0;
+        bool tie = false;
+        for (int d = 0; d < nc; ++d) {
+            const uint32_t ok = cand_key[d];
+            const int oe = cand_e[d];
+            rank += (ok > mk) || (ok == mk && oe < me);
+            tie |= (ok == mk && d != c);
+        }
+        if (rank < K) {
+            s_order[rank] = me;
+            if (tie) s_flag = 1;
+        }
+    }
+    __syncthreads();
+    if (s_flag) {
+        if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
+        return;
+    }
+    if (tid < K) {
+        const int e = s_order[tid];
+        const int i = e / nR, j = e - i * nR;
+        P.corr_v[job * kTopCorrMinu + tid] = Ssm[i * ld + j];
+        P.corr_ij[job * kTopCorrMinu + tid] = ((uint32_t)i << 16) | (uint32_t)j;
+    }
+    if (tid == 0) P.corr_n[job] = K;
+}
+
+// Jobs whose order depends on how libstdc++'s introsort permutes equal keys.
+__host__ __device__ inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np) {
+    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(uint16_t) * (size_t)max_nL * max_np + 16;
+}
+
+__global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelectParams P, unsigned long long* replay_count) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSelThreads / 32;
+    float* Ssm = reinterpret_cast<float*>(smem);
+    float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);
+    float* rsum = lsum + P.max_nL;
+    uint16_t* y = reinterpret_cast<uint16_t*>(rsum + P.max_np);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(Ssm);
+    const int n_jobs = *P.slow_count;
+    for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        const size_t job = (size_t)P.slow_jobs[jb];
+        const int slot = (int)(job % 3);
+        const size_t pair = job / 3;
+        const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+        const int nR = P.minu_n[P.g0 + tl];
+        const int nL = P.slot_n[q * 3 + slot];
+        const int np = (nR + 3) & ~3, ld = np + 1;
+        const float* Sg = P.S + job * P.job_stride;
+        __syncthreads();
+        for (int i = warp; i < nL; i += NW)
+            for (int j = lane; j < nR; j += 32) Ssm[i * ld + j] = Sg[(size_t)i * np + j];
+        __syncthreads();
+        for (int j = tid; j < nR; j += kSelThreads) {
+            float acc = Ssm[j];
+            for (int i = 1; i < nL; ++i) acc = f_add(acc, Ssm[i * ld + j]);
+            rsum[j] = acc;
+        }
+        for (int i = tid; i < nL; i += kSelThreads) {
+            float acc = Ssm[i * ld];
+            for (int j = 1; j < nR; ++j) acc = f_add(acc, Ssm[i * ld + j]);
+            lsum[i] = acc;
+        }
+        __syncthreads();
+        for (int i = warp; i < nL; i += NW)
+            for (int j = lane; j < nR; j += 32) {
+                const float s = Ssm[i * ld + j];
+                keys[i * ld + j] = (s != 0.0f) ? exact_key(s, lsum[i], rsum[j]) : 0u;
+            }
+        __syncthreads();
+        const int M = nL * nR;
+        const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
+        if (tid == 0) {
+            const uint32_t* kk = keys;
+            const int nRr = nR, ldd = ld;
+            auto keyfn = [kk, nRr, ldd](int e) -> uint32_t {
+                const int i = e / nRr;
+                return kk[i * ldd + (e - i * nRr)];
+            };
+            std_sort_desc_prefix(keyfn, y, M, K);
+            atomicAdd(replay_count, 1ull);
+        }
+        __syncthreads();
+        if (tid < K) {
+            const int e = y[tid];
+            const int i = e / nR, j = e - i * nR;
+            P.corr_v[job * kTopCorrMinu + tid] = Sg[(size_t)i * np + j];
+            P.corr_ij[job * kTopCorrMinu + tid] = ((uint32_t)i << 16) | (uint32_t)j;
+        }
+        if (tid == 0) P.corr_n[job] = K;
+    }
+}
+
+}  // namespace lafis
