@@ -189,6 +189,13 @@ typedef struct {
     float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events between the
                                  launches): 0 tex_rowmax, 1 minu_sim, 2 minu_select (+slow), 3 graph_minu
                                  (sparse + dense), 4 graph_tex (sparse + dense), 5 fuse + rank lists */
+    /* cumulative exactness bookkeeping since the context was created */
+    uint64_t minu_replays;    /* top-120 selections that needed the introsort replay (ties) */
+    uint64_t tex_replays;     /* top-200 row selections that needed the introsort replay */
+    uint64_t tex_queued;      /* texture row-max: (row, column) candidates queued by the integer filter */
+    uint64_t tex_exact;       /* ... of which re-evaluated exactly in fp32 */
+    uint64_t tex_overflow;    /* ... (warp, template) visits whose queue overflowed: evaluated exactly in full */
+    uint64_t tex_templates;   /* ... (warp, template) visits in total */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */

@@ -50,6 +50,7 @@ struct SparseWork {
     unsigned short y[G::MAXP];    // candidates in std::sort order
     unsigned short sel[G::MAXP];  // accepted candidates, acceptance order
     unsigned char cols[G::CAP];
+    unsigned char rowj[G::NT / 32][G::MAXP];  // per-warp scratch: columns that passed the cheap test
     float f;
     int overflow, tie, nsel;
     // orientation stage (<= 32 survivors), only touched when the introsort replay is needed
@@ -57,7 +58,31 @@ struct SparseWork {
     unsigned short y2[32];
 };
 
-// H entry of the distance-consistency graph for candidates a, b (symmetric in a, b).
+// Cheap, conservative pre-test of "H[a][b] may be non-zero" evaluated for ALL pairs; the exact entry is
+// then computed only for the survivors (~9 % of the pairs of a non-mated print), compacted so that the
+// expensive correctly-rounded square roots and divisions run on full warps.
+template <bool LOOKUP>
+__device__ __forceinline__ bool pair_may_connect(short2 la, short2 lb, short2 ra, short2 rb, const float* __restrict__ table) {
+    if (LOOKUP) {  // matcher.cpp:1246-1266: the whole test up to "dist > d_thr" is cheap here
+        const int dx1 = abs((int)la.x - (int)lb.x), dx2 = abs((int)ra.x - (int)rb.x);
+        const int dy1 = abs((int)la.y - (int)lb.y), dy2 = abs((int)ra.y - (int)rb.y);
+        if ((dx1 >= kTableN) | (dx2 >= kTableN) | (dy1 >= kTableN) | (dy2 >= kTableN)) return false;
+        const float d1 = __ldg(table + dx1 * kTableN + dy1);
+        const float d2 = __ldg(table + dx2 * kTableN + dy2);
+        return !(fabsf(f_sub(d1, d2)) > 30.0f);
+    } else {
+        // |d1 - d2| <= 30.04  <=>  s1 + s2 - 30.04^2 <= 2 sqrt(s1 s2), with s = d^2 an exact integer below
+        // 2^24.  Rounding moves the comparison by < 0.2 squared pixels (coordinates are below 2^11), the
+        // margin over 30^2 is 2.4: nothing with |d1 - d2| <= 30 is rejected here.
+        const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
+        const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
+        const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);
+        const float t = s1 + s2 - 902.4f;
+        return t <= 0.0f || t * t <= 4.0f * s1 * s2;
+    }
+}
+
+// H entry of the distance-consistency graph for candidates a, b (symmetric in a, b), exact.
 template <bool LOOKUP>
 __device__ __forceinline__ float pair_h(short2 la, short2 lb, short2 ra, short2 rb, const float* __restrict__ table) {
     float d1, d2;
@@ -70,16 +95,8 @@ __device__ __forceinline__ float pair_h(short2 la, short2 lb, short2 ra, short2 
     } else {  // matcher.cpp:1372-1384
         const float dx1 = (float)((int)la.x - (int)lb.x), dx2 = (float)((int)ra.x - (int)rb.x);
         const float dy1 = (float)((int)la.y - (int)lb.y), dy2 = (float)((int)ra.y - (int)rb.y);
-        const float s1 = f_add(f_mul(dx1, dx1), f_mul(dy1, dy1));  // exact: integers below 2^24
-        const float s2 = f_add(f_mul(dx2, dx2), f_mul(dy2, dy2));
-        // cheap rejection with the approximate square root (relative error <= 2^-22 on values
-        // <= 1200 px): nothing within 0.01 px of the 30 px threshold is decided here
-        float a1, a2;
-        asm("sqrt.approx.f32 %0, %1;" : "=f"(a1) : "f"(s1));
-        asm("sqrt.approx.f32 %0, %1;" : "=f"(a2) : "f"(s2));
-        if (fabsf(a1 - a2) > 30.01f) return 0.0f;
-        d1 = __fsqrt_rn(s1);
-        d2 = __fsqrt_rn(s2);
+        d1 = __fsqrt_rn(f_add(f_mul(dx1, dx1), f_mul(dy1, dy1)));
+        d2 = __fsqrt_rn(f_add(f_mul(dx2, dx2), f_mul(dy2, dy2)));
     }
     const float dist = fabsf(f_sub(d1, d2));
     if (dist > 30.0f) return 0.0f;
@@ -133,24 +150,39 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
         int used = 0;
         bool over = false;
         const unsigned lt_mask = (1u << lane) - 1u;
+        unsigned char* rowj = w.rowj[warp];
         for (int i = warp; i < num; i += NW) {
             const short2 la = w.lxy[i], ra = w.rxy[i];
-            int len = 0;
+            // pass 1: columns that may connect to row i, ascending
+            int cnt = 0;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const int j = lane + 32 * c;
-                float h = 0.0f;
-                if (j < num && j != i) h = pair_h<LOOKUP>(la, clxy[c], ra, crxy[c], table);
-                const unsigned m = __ballot_sync(0xffffffffu, h > 0.0f);
-                if (m) {
-                    const int pos = used + len + __popc(m & lt_mask);
-                    if (h > 0.0f && pos < CAPW) {
-                        w.vals[wbase + pos] = h;
-                        w.cols[wbase + pos] = (unsigned char)j;
-                    }
-                    len += __popc(m);
-                }
+                const bool pass = j < num && j != i && pair_may_connect<LOOKUP>(la, clxy[c], ra, crxy[c], table);
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
+                cnt += __popc(m);
             }
+            __syncwarp();
+            // pass 2: exact entries of the survivors, compacted again (an exact entry can still be 0)
+            int len = 0;
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const int idx = b0 + lane;
+                float h = 0.0f;
+                int j = 0;
+                if (idx < cnt) {
+                    j = rowj[idx];
+                    h = pair_h<LOOKUP>(la, w.lxy[j], ra, w.rxy[j], table);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, h > 0.0f);
+                const int pos = used + len + __popc(m & lt_mask);
+                if (h > 0.0f && pos < CAPW) {
+                    w.vals[wbase + pos] = h;
+                    w.cols[wbase + pos] = (unsigned char)j;
+                }
+                len += __popc(m);
+            }
+            __syncwarp();
             if (used + len > CAPW) over = true;
             if (lane == 0) {
                 w.row_start[i] = (unsigned short)(wbase + used);

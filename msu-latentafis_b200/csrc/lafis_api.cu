@@ -109,6 +109,7 @@ struct lafis_ctx {
     uint64_t algo_bytes = 0;
 
     // work buffers
+    DevBuf<float> tex_lut, tex_scale;  // fp32 PQ distance tables of the latent batch (K1) + per-row quantiser scales
     DevBuf<float> rowmax_val;
     DevBuf<uint16_t> rowmax_j;
     DevBuf<float> corr_v;
@@ -125,7 +126,8 @@ struct lafis_ctx {
     DevBuf<HitDev> hits;
     DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
     int* d_job_counter = nullptr;
-    unsigned long long* d_slow = nullptr;  // [2] introsort replays: minutiae top-120, texture top-200
+    unsigned long long* d_slow = nullptr;  // [8] counters: 0 minutiae introsort replays, 1 texture top-200 replays,
+                                           //     4..7 texture row-max: queued, exact evaluations, overflowed, templates
 
     lafis_stats stats{};
 };
@@ -201,7 +203,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_ov_count, 2 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_slow_count, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_slow, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_slow, 8 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) {
         // matcher.cpp:49-56: table[i*50+j] = (float)sqrt((16 i)^2 + (16 j)^2), square root in double
         std::vector<float> table(kTableN * kTableN);
@@ -211,7 +213,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
         ok = cudaMemcpy(c->d_table, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemcpy(c->d_codebook, codewords, sizeof(float) * kSubs * kClusters * kSubDim,
                               cudaMemcpyHostToDevice) == cudaSuccess;
-        ok = ok && cudaMemset(c->d_slow, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(c->d_slow, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
         TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
         TRY(cudaFuncSetAttribute(minu_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(minu_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -274,6 +276,8 @@ void lafis_destroy(lafis_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_gallery(c);
     c->rowmax_val.release();
+    c->tex_lut.release();
+    c->tex_scale.release();
     c->rowmax_j.release();
     c->corr_v.release();
     c->corr_ij.release();
@@ -642,7 +646,7 @@ int lafis_latents_from_packed(lafis_ctx* c, const lafis_packed_latents* p, lafis
         L->tex_n[q] = ntp;
         max_t = std::max(max_t, ntp);
     }
-    L->lt_stride = std::max(8, round_up(max_t, 8));
+    L->lt_stride = std::max(kRowTile, round_up(max_t, kRowTile));
     uint32_t off = 0;
     for (int s = 0; s < 3 * n; ++s) {
         const int q = s / 3, slot = s % 3;
@@ -825,6 +829,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     chunk_sz = std::max<size_t>(chunk_sz, 1);
     const int n_chunk_max = (int)chunk_sz;
 
+    LAFIS_CUDA(c, c->tex_lut.reserve((size_t)Q * lt * 4096));
+    LAFIS_CUDA(c, c->tex_scale.reserve((size_t)Q * lt));
     LAFIS_CUDA(c, c->rowmax_val.reserve((size_t)Q * n_chunk_max * lt));
     LAFIS_CUDA(c, c->rowmax_j.reserve((size_t)Q * n_chunk_max * lt));
     LAFIS_CUDA(c, c->corr_v.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
@@ -848,17 +854,29 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     int chunk_id = 0;
     auto stamp = [&](int i) { cudaEventRecord(c->stage_ev[6 * chunk_id + i], st); };
 
+    {   // ---- K1: fp32 distance tables of the batch, once per match ----
+        TexLutParams P;
+        P.lat_des = D.tex_des;
+        P.lat_nt = D.tex_n;
+        P.lt_stride = L->lt_stride;
+        P.Q = Q;
+        P.codebook = c->d_codebook;
+        P.lut = c->tex_lut.p;
+        P.row_scale = c->tex_scale.p;
+        tex_lut_kernel<<<dim3(L->lt_stride, Q), 256, 0, st>>>(P);
+        c->stats.kernel_launches += 1;
+    }
     for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
         const int n_chunk = std::min(n_chunk_max, G - g0);
         // ---- K1 + K2 + K3a ----
         stamp(0);
         {
             TexRowmaxParams P;
-            P.lat_des = D.tex_des;
+            P.lut = c->tex_lut.p;
+            P.row_scale = c->tex_scale.p;
             P.lat_nt = D.tex_n;
             P.lt_stride = L->lt_stride;
             P.Q = Q;
-            P.codebook = c->d_codebook;
             P.tex_off = c->gal.tex_off;
             P.codes = c->gal.tex_codes;
             P.g0 = g0;
@@ -871,6 +889,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.rowmax_val = c->rowmax_val.p;
             P.rowmax_j = c->rowmax_j.p;
             P.job_counter = c->d_job_counter;
+            P.counters = c->d_slow + 4;
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_job_counter, 0, sizeof(int), st));
             const int grid = std::min(c->sm_count, Q * n_rowtiles * slices);
             tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, st>>>(P);
@@ -1035,6 +1054,15 @@ static void collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&t, c->stage_ev[6 * c->stage_chunks], c->stage_ev[6 * c->stage_chunks + 1]);
     ms[5] = t;
     std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
+    unsigned long long cnt[8];
+    if (cudaMemcpy(cnt, c->d_slow, sizeof cnt, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        c->stats.minu_replays = cnt[0];
+        c->stats.tex_replays = cnt[1];
+        c->stats.tex_queued = cnt[4];
+        c->stats.tex_exact = cnt[5];
+        c->stats.tex_overflow = cnt[6];
+        c->stats.tex_templates = cnt[7];
+    }
 }
 
 int lafis_match_device(lafis_ctx* c, lafis_latents* L, int topk, const void** d_hits, const float** d_all_scores) {

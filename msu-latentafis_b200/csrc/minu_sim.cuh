@@ -257,8 +257,30 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
     __shared__ int s_order[kTopCorrMinu];
 
     const float* Sg = P.S + job * P.job_stride;
-    for (int i = warp; i < nL; i += NW)
-        for (int j = lane; j < nR; j += 32) Ssm[i * ld + j] = Sg[(size_t)i * np + j];
+    {   // S is [nL][np] with np % 4 == 0: 16-byte loads, batches of four in flight per thread
+        const float4* Sg4 = reinterpret_cast<const float4*>(Sg);
+        const int n4 = nL * (np >> 2), row4 = np >> 2;
+        for (int e0 = tid; e0 < n4; e0 += 4 * kSelThreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kSelThreads;
+                v[u] = (e < n4) ? __ldcs(Sg4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kSelThreads;
+                if (e < n4) {
+                    const int i = e / row4, c4 = e - i * row4;
+                    float* d = Ssm + i * ld + 4 * c4;
+                    d[0] = v[u].x;
+                    d[1] = v[u].y;
+                    d[2] = v[u].z;
+                    d[3] = v[u].w;
+                }
+            }
+        }
+    }
     for (int b = tid; b < kSelBins; b += kSelThreads) hist[b] = 0;
     if (tid == 0) {
         s_ncand = 0;
@@ -296,8 +318,9 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
             for (int j = lane; j < nR; j += 32) {
                 const float s = Ssm[i * ld + j];
                 if (s > 0.0f) {
-                    const uint32_t bits = __float_as_uint(approx_key(s, l, rsum[j]));
-                    atomicAdd(&hist[min(bits >> 20, (uint32_t)(kSelBins - 1))], 1);
+                    const float a = approx_key(s, l, rsum[j]);
+                    Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
+                    atomicAdd(&hist[min(__float_as_uint(a) >> 20, (uint32_t)(kSelBins - 1))], 1);
                     ++npos;
                 }
             }
@@ -344,11 +367,11 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
         for (int i = warp; i < nL; i += NW) {
             const float l = lsum[i];
             for (int j = lane; j < nR; j += 32) {
-                const float s = Ssm[i * ld + j];
-                if (s > 0.0f && approx_key(s, l, rsum[j]) >= thr) {
+                const float a = Ssm[i * ld + j];  // 0 where S was not positive
+                if (a > 0.0f && a >= thr) {
                     const int pos = atomicAdd(&s_ncand, 1);
                     if (pos < kSelMaxCand) {
-                        cand_key[pos] = exact_key(s, l, rsum[j]);
+                        cand_key[pos] = exact_key(__ldg(Sg + (size_t)i * np + j), l, rsum[j]);
                         cand_e[pos] = i * nR + j;
                     }
                 }
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
     if (tid < K) {
         const int e = s_order[tid];
         const int i = e / nR, j = e - i * nR;
-        P.corr_v[job * kTopCorrMinu + tid] = Ssm[i * ld + j];
+        P.corr_v[job * kTopCorrMinu + tid] = __ldg(Sg + (size_t)i * np + j);
         P.corr_ij[job * kTopCorrMinu + tid] = ((uint32_t)i << 16) | (uint32_t)j;
     }
     if (tid == 0) P.corr_n[job] = K;
