@@ -810,7 +810,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     // ---- geometry ----
     const int maxL = std::max(1, L->max_slot_n), maxLp = (maxL + 3) & ~3;
     const int maxNp = std::max(4, (c->max_nR + 3) & ~3);
-    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 128;
+    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 160;
     int b_double = 1;
     if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
     const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);

@@ -58,7 +58,7 @@ struct MinuSimParams {
     int g0, n_chunk;
     // shared-memory geometry (floats)
     int a_slot_stride;  // one latent slot: 96 * max padded slot count + 16
-    int b_buf_stride;   // one gallery block: 96 * max padded template count + 128
+    int b_buf_stride;   // one gallery block: 96 * max padded template count + 160
     int b_double;       // two gallery buffers
     // output: S[job][i * np + j], job = (q * n_chunk + tl) * 3 + slot
     float* S;
@@ -67,6 +67,50 @@ struct MinuSimParams {
 
 __host__ __device__ inline size_t minu_sim_smem_bytes(int a_slot_stride, int b_buf_stride, int b_double) {
     return sizeof(float) * ((size_t)3 * a_slot_stride + (size_t)(b_double ? 2 : 1) * b_buf_stride);
+}
+
+// One warp tile of S = max(0, A.B^T): rows i0..i0+7 of this thread (16 per warp), columns
+// jbase + {lj*4..+3, 64+lj*4..+3} and, when WIDE, 128 + {lj*2, lj*2+1}.  k ascending, unfused.
+template <bool WIDE>
+__device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, const float* __restrict__ Bt, int npR, int lj,
+                                         int jbase, int i0, int nL, float* __restrict__ out) {
+    constexpr int NC = WIDE ? 10 : 8;
+    const int ja = jbase + lj * 4, jb = ja + 64, jc = jbase + 128 + lj * 2;
+    const float* bpa = Bt + ja;
+    const float* bpb = Bt + jb;
+    const float* bpc = Bt + jc;
+    float acc[8][NC];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < NC; ++b) acc[a][b] = 0.0f;
+#pragma unroll 2
+    for (int k = 0; k < 96; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(ap + k * npL);
+        const float4 a1 = *reinterpret_cast<const float4*>(ap + k * npL + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
+        const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
+        float2 b2 = make_float2(0.f, 0.f);
+        if (WIDE) b2 = *reinterpret_cast<const float2*>(bpc + k * npR);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < NC; ++b) acc[a][b] = f_add(acc[a][b], f_mul(av[a], bv[b]));
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = i0 + a;
+        if (i >= nL) continue;
+        float v[NC];
+#pragma unroll
+        for (int b = 0; b < NC; ++b) v[b] = acc[a][b] < 0.0f ? 0.0f : acc[a][b];  // matcher.cpp:449-450
+        float* row = out + (size_t)i * npR;
+        if (ja < npR) *reinterpret_cast<float4*>(row + ja) = make_float4(v[0], v[1], v[2], v[3]);
+        if (jb < npR) *reinterpret_cast<float4*>(row + jb) = make_float4(v[4], v[5], v[6], v[7]);
+        if (WIDE && jc < npR) *reinterpret_cast<float2*>(row + jc) = make_float2(v[8], v[9]);
+    }
 }
 
 __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams P) {
@@ -132,57 +176,26 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
             __syncthreads();
             if (!live) continue;
 
-            // tile list over the three slots
+            // tile list over the three slots.  A warp tile is 16 rows x 128 columns (8 x 8 per thread) or,
+            // for templates of 129..160 minutiae, 16 x 160 (8 x 10 per thread) so that one tile still
+            // spans the whole template.
+            const bool wide = nR > 128 && nR <= 160;
+            const int tiles_jj = wide ? 1 : tiles_j;
             int t0[4];
             t0[0] = 0;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_j;
+            for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_jj;
             for (int t = warp; t < t0[3]; t += NW) {
                 const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
                 const int tt = t - t0[s];
-                const int ti = tt / tiles_j, tj = tt - ti * tiles_j;
+                const int ti = tt / tiles_jj, tj = tt - ti * tiles_jj;
                 const int nL = P.slot_n[q * 3 + s];
                 const int npL = (nL + 3) & ~3;
                 const int i0 = ti * 16 + li * 8;
-                const int ja = tj * 128 + lj * 4, jb = ja + 64;
                 const float* ap = A + (size_t)s * P.a_slot_stride + i0;
-                const float* bpa = Bt + ja;
-                const float* bpb = Bt + jb;
-                float acc[8][8];
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
-#pragma unroll 2
-                for (int k = 0; k < 96; ++k) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * npL);
-                    const float4 a1 = *reinterpret_cast<const float4*>(ap + k * npL + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) acc[a][b] = f_add(acc[a][b], f_mul(av[a], bv[b]));
-                }
                 float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int i = i0 + a;
-                    if (i >= nL) continue;
-                    float4 v0, v1;
-                    v0.x = acc[a][0] < 0.0f ? 0.0f : acc[a][0];  // matcher.cpp:449-450
-                    v0.y = acc[a][1] < 0.0f ? 0.0f : acc[a][1];
-                    v0.z = acc[a][2] < 0.0f ? 0.0f : acc[a][2];
-                    v0.w = acc[a][3] < 0.0f ? 0.0f : acc[a][3];
-                    v1.x = acc[a][4] < 0.0f ? 0.0f : acc[a][4];
-                    v1.y = acc[a][5] < 0.0f ? 0.0f : acc[a][5];
-                    v1.z = acc[a][6] < 0.0f ? 0.0f : acc[a][6];
-                    v1.w = acc[a][7] < 0.0f ? 0.0f : acc[a][7];
-                    if (ja < npR) *reinterpret_cast<float4*>(out + (size_t)i * npR + ja) = v0;
-                    if (jb < npR) *reinterpret_cast<float4*>(out + (size_t)i * npR + jb) = v1;
-                }
+                if (wide) sim_tile<true>(ap, npL, Bt, npR, lj, 0, i0, nL, out);
+                else sim_tile<false>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out);
             }
         }
         __syncthreads();  // everyone is done with this gallery block before it is overwritten
