@@ -63,13 +63,17 @@ struct SparseWork {
 // expensive correctly-rounded square roots and divisions run on full warps.
 template <bool LOOKUP>
 __device__ __forceinline__ bool pair_may_connect(short2 la, short2 lb, short2 ra, short2 rb, const float* __restrict__ table) {
-    if (LOOKUP) {  // matcher.cpp:1246-1266: the whole test up to "dist > d_thr" is cheap here
-        const int dx1 = abs((int)la.x - (int)lb.x), dx2 = abs((int)ra.x - (int)rb.x);
-        const int dy1 = abs((int)la.y - (int)lb.y), dy2 = abs((int)ra.y - (int)rb.y);
-        if ((dx1 >= kTableN) | (dx2 >= kTableN) | (dy1 >= kTableN) | (dy2 >= kTableN)) return false;
-        const float d1 = __ldg(table + dx1 * kTableN + dy1);
-        const float d2 = __ldg(table + dx2 * kTableN + dy2);
-        return !(fabsf(f_sub(d1, d2)) > 30.0f);
+    if (LOOKUP) {
+        // matcher.cpp:1246-1266 with table[dx][dy] = fl(16 sqrt(dx^2 + dy^2)): |d1 - d2| <= 30 needs
+        // (16 sqrt(s1) - 16 sqrt(s2))^2 <= 900, i.e. 64 (s1 + s2) - 225 <= 128 sqrt(s1 s2) with the integers
+        // s = dx^2 + dy^2 < 5000.  Tested in integers with the 225 widened to 232 (the table entries are
+        // rounded to fp32: relative 6e-8 on values <= 1110, far inside that margin); no table load.
+        const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
+        const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
+        if ((abs(dx1) >= kTableN) | (abs(dx2) >= kTableN) | (abs(dy1) >= kTableN) | (abs(dy2) >= kTableN)) return false;
+        const int s1 = dx1 * dx1 + dy1 * dy1, s2 = dx2 * dx2 + dy2 * dy2;
+        const int t = 64 * (s1 + s2) - 232;  // < 2^20
+        return t <= 0 || (long long)t * t <= 16384ll * s1 * s2;
     } else {
         // |d1 - d2| <= 30.04  <=>  s1 + s2 - 30.04^2 <= 2 sqrt(s1 s2), with s = d^2 an exact integer below
         // 2^24.  Rounding moves the comparison by < 0.2 squared pixels (coordinates are below 2^11), the

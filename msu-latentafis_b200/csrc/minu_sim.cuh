@@ -32,7 +32,7 @@ namespace lafis {
 
 constexpr int kSimThreads = 512;
 constexpr int kSelThreads = 256;
-constexpr int kSelMaxCand = 512;
+constexpr int kSelMaxCand = 384;
 constexpr int kSelBins = 1024;  // float bits >> 20 of values in (0, 1]
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -475,15 +475,15 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
         __syncthreads();
         const int M = nL * nR;
         const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
-        if (tid == 0) {
+        if (warp == 0) {  // replay of libstdc++'s introsort, warp-cooperative (stdsort_emul.h)
             const uint32_t* kk = keys;
             const int nRr = nR, ldd = ld;
             auto keyfn = [kk, nRr, ldd](int e) -> uint32_t {
                 const int i = e / nRr;
                 return kk[i * ldd + (e - i * nRr)];
             };
-            std_sort_desc_prefix(keyfn, y, M, K);
-            atomicAdd(replay_count, 1ull);
+            warp_std_sort_desc_prefix(keyfn, y, M, K);
+            if (lane == 0) atomicAdd(replay_count, 1ull);
         }
         __syncthreads();
         if (tid < K) {

@@ -193,4 +193,120 @@ LAFIS_SORT_HD inline void std_sort_desc_prefix(KeyFn key, IdxT* y, int n, int ne
     s.sort_prefix(n, need);
 }
 
+
+#if defined(__CUDACC__)
+// Warp-cooperative replay: the same algorithm, executed by all 32 lanes of a warp in lock step (every
+// lane sees the same shared-memory contents and takes the same branches).  The two scanning loops of the
+// Hoare partition - where almost all of the O(n) work is - examine 32 positions per step with a ballot;
+// everything that writes is done by lane 0 between __syncwarp()s.  `y` must be in shared memory.
+template <typename KeyFn, typename IdxT>
+struct WarpStdSortEmu {
+    KeyFn key;
+    IdxT* y;
+    int lane;
+
+    __device__ bool before(IdxT a, IdxT b) const { return key((int)a) > key((int)b); }
+    __device__ void swp(int a, int b) {
+        if (lane == 0) {
+            IdxT t = y[a];
+            y[a] = y[b];
+            y[b] = t;
+        }
+        __syncwarp();
+    }
+    // first p >= lo with !before(y[p], piv); std::sort's pivot choice guarantees one below `limit`
+    __device__ int scan_up(int lo, IdxT piv, int limit) {
+        for (;;) {
+            const int p = lo + lane;
+            const bool stop = (p >= limit) || !before(y[p], piv);
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return lo + __ffs(m) - 1;
+            lo += 32;
+        }
+    }
+    // first p <= hi (descending) with !before(piv, y[p])
+    __device__ int scan_down(int hi, IdxT piv, int limit) {
+        for (;;) {
+            const int p = hi - lane;
+            const bool stop = (p < limit) || !before(piv, y[p]);
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) return hi - (__ffs(m) - 1);
+            hi -= 32;
+        }
+    }
+    __device__ int partition_pivot(int first, int last) {
+        const int mid = first + (last - first) / 2;
+        const int a = first + 1, b = mid, c = last - 1;
+        if (before(y[a], y[b])) {
+            if (before(y[b], y[c])) swp(first, b);
+            else if (before(y[a], y[c])) swp(first, c);
+            else swp(first, a);
+        } else if (before(y[a], y[c])) swp(first, a);
+        else if (before(y[b], y[c])) swp(first, c);
+        else swp(first, b);
+        const IdxT piv = y[first];
+        int lo = first + 1, hi = last;
+        for (;;) {
+            lo = scan_up(lo, piv, last);
+            --hi;
+            hi = scan_down(hi, piv, first);
+            if (!(lo < hi)) return lo;
+            swp(lo, hi);
+            ++lo;
+        }
+    }
+    __device__ void sort_prefix(int n, int need) {
+        if (n <= 0) return;
+        if (need > n) need = n;
+        int lg = 0;
+        for (int m = n; m > 1; m >>= 1) ++lg;
+        StdSortEmu<KeyFn, IdxT> seq{key, y};  // heap sort / insertion sort: lane 0 only
+        struct Frame {
+            int first, last, depth;
+        };
+        Frame stack[72];
+        int sp = 0, done_to = 0;
+        stack[sp++] = Frame{0, n, 2 * lg};
+        while (sp > 0) {
+            Frame f = stack[--sp];
+            if (f.first >= need) continue;
+            while (f.last - f.first > 16) {
+                if (f.depth == 0) {
+                    if (lane == 0) seq.heap_sort(f.first, f.last);
+                    __syncwarp();
+                    break;
+                }
+                --f.depth;
+                const int cut = partition_pivot(f.first, f.last);
+                if (cut < need) stack[sp++] = Frame{cut, f.last, f.depth};
+                f.last = cut;
+            }
+            if (f.last > done_to) done_to = f.last;
+        }
+        if (lane == 0) {
+            if (n > 16) {
+                int E = done_to;
+                if (E < 16) E = 16;
+                if (E > n) E = n;
+                seq.insertion_sort(0, 16);
+                for (int i = 16; i < E; ++i) seq.unguarded_linear_insert(i);
+            } else {
+                seq.insertion_sort(0, n);
+            }
+        }
+        __syncwarp();
+    }
+};
+
+// first `need` positions, whole warp cooperating; y in shared memory, every lane passes the same arguments
+template <typename KeyFn, typename IdxT>
+__device__ inline void warp_std_sort_desc_prefix(KeyFn key, IdxT* y, int n, int need) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) y[i] = (IdxT)i;
+    __syncwarp();
+    WarpStdSortEmu<KeyFn, IdxT> s{key, y, lane};
+    s.sort_prefix(n, need);
+}
+#endif
+
 }  // namespace lafis

@@ -206,14 +206,7 @@ __global__ void __launch_bounds__(kRowmaxThreads, 1) tex_rowmax_kernel(TexRowmax
             const int n = (int)(P.tex_off[g + 1] - base);
             if (n <= 0) continue;
             ++n_tpl;
-            if (lane < kRowTile) {
-                ws.best[lane] = 0ull;
-                ws.rmin[lane] = 0xffffu;
-            }
-            if (lane == 0) {
-                ws.count = 0;
-                ws.overflow = 0;
-            }
+            if (lane < kRowTile) ws.best[lane] = 0ull;
             __syncwarp();
             const uint4* cp = P.codes + base + jl;
 
@@ -244,22 +237,32 @@ __global__ void __launch_bounds__(kRowmaxThreads, 1) tex_rowmax_kernel(TexRowmax
                 }
             };
 
-            // warm-up: minima over the first 32 points, nothing queued
-            for (int j0 = 0; j0 < n && j0 < 32; j0 += 16) {
-                uint32_t dq[8];
-                batch(__ldg(cp + j0), dq);
-                if (j0 + jl < n) {
+            // Per-row thresholds live in registers and are refreshed from the warp's shared minima every four
+            // batches.  A threshold is (smallest Dq seen so far) + kWindow, so a stale value is only ever
+            // too large: it can queue too much, never miss a candidate.
+            const unsigned hf_mask = hf ? 0xaaaaaaaau : 0x55555555u;
+            uint32_t thr[8];
+            {   // warm-up: minima over the first 32 points, nothing queued
+                uint32_t lmin[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if ((row_live >> r) & 1u) atomicMin(&ws.rmin[hf * 8 + r], dq[r]);
+                for (int r = 0; r < 8; ++r) lmin[r] = 0xffffu;
+                for (int j0 = 0; j0 < n && j0 < 32; j0 += 16) {
+                    uint32_t dq[8];
+                    batch(__ldg(cp + j0), dq);
+                    if (j0 + jl < n) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) lmin[r] = min(lmin[r], dq[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t mn = __reduce_min_sync(hf_mask, lmin[r]);
+                    thr[r] = mn + kWindow;
+                    if (lane < 2) ws.rmin[hf * 8 + r] = mn;  // lanes 0 / 1 publish rows 0..7 / 8..15
                 }
             }
+            if (lane == 0) ws.count = 0;
             __syncwarp();
-            uint32_t thr[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) thr[r] = ((row_live >> r) & 1u) ? ws.rmin[hf * 8 + r] + kWindow : 0u;
-            // padding rows: dq >= 0 is never <= thr - 1 ... handled by the row_live test below
-
             uint4 cnext = __ldg(cp);
             int since_refresh = 0;
             for (int j0 = 0; j0 < n; j0 += 16) {
@@ -271,11 +274,10 @@ __global__ void __launch_bounds__(kRowmaxThreads, 1) tex_rowmax_kernel(TexRowmax
                 if (j < n) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        if (((row_live >> r) & 1u) && dq[r] <= thr[r]) {
+                        if (dq[r] <= thr[r] && ((row_live >> r) & 1u)) {  // rare: ~6 per row and template
                             const int slot = atomicAdd(&ws.count, 1);
                             if (slot < kQueueCap) ws.queue[slot] = (uint32_t)(hf * 8 + r) | ((uint32_t)j << 4) | (dq[r] << 14);
-                            else ws.overflow = 1;
-                            if (dq[r] + kWindow < thr[r]) {
+                            if (dq[r] + kWindow < thr[r]) {  // a new minimum: share it through shared memory
                                 thr[r] = dq[r] + kWindow;
                                 atomicMin(&ws.rmin[hf * 8 + r], dq[r]);
                             }
@@ -284,11 +286,16 @@ __global__ void __launch_bounds__(kRowmaxThreads, 1) tex_rowmax_kernel(TexRowmax
                 }
                 if (++since_refresh == 4) {  // pick up minima found by the other lanes
                     since_refresh = 0;
-                    __syncwarp();
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if ((row_live >> r) & 1u) thr[r] = min(thr[r], ws.rmin[hf * 8 + r] + kWindow);
+                    for (int r = 0; r < 8; ++r) thr[r] = min(thr[r], ws.rmin[hf * 8 + r] + kWindow);
                 }
+            }
+            __syncwarp();
+            // queue state
+            if (lane == 0) {
+                const int count = ws.count;
+                ws.overflow = count > kQueueCap;
+                ws.count = min(count, kQueueCap);
             }
             __syncwarp();
 
