@@ -87,6 +87,9 @@ struct lafis_latents {
 struct lafis_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_b = nullptr;  // texture chain runs here, concurrently with the minutiae chain on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool two_streams = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_ev;  // 6 per pipeline chunk + 2 for the tail, grown on demand
     int stage_chunks = 0;               // chunks of the last match
@@ -197,6 +200,10 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     bool ok = true;
     TRY(cudaSetDevice(device));
     ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e2 = getenv("LAFIS_STREAMS")) c->two_streams = atoi(e2) >= 2;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
@@ -301,6 +308,9 @@ void lafis_destroy(lafis_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
+    if (c->stream_b) cudaStreamDestroy(c->stream_b);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -843,16 +853,23 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
     LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
 
-    // stage time stamps: 6 per chunk (before each of the 5 stages + after the last) and 2 for the tail
+    // stage time stamps: a (start, end) pair for each of the 5 stages of a chunk, recorded on the stage's own
+    // stream, and 2 for the tail
     const int n_chunks = (G + n_chunk_max - 1) / n_chunk_max;
-    while ((int)c->stage_ev.size() < 6 * n_chunks + 2) {
+    while ((int)c->stage_ev.size() < 10 * n_chunks + 2) {
         cudaEvent_t e;
         LAFIS_CUDA(c, cudaEventCreate(&e));
         c->stage_ev.push_back(e);
     }
     c->stage_chunks = n_chunks;
     int chunk_id = 0;
-    auto stamp = [&](int i) { cudaEventRecord(c->stage_ev[6 * chunk_id + i], st); };
+    cudaStream_t sb = c->two_streams ? c->stream_b : st;
+    auto begin = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[10 * chunk_id + 2 * stage], s_); };
+    auto end = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[10 * chunk_id + 2 * stage + 1], s_); };
+    if (c->two_streams) {  // the texture chain starts once the latent batch is in HBM
+        LAFIS_CUDA(c, cudaEventRecord(c->ev_fork, st));
+        LAFIS_CUDA(c, cudaStreamWaitEvent(sb, c->ev_fork, 0));
+    }
 
     {   // ---- K1: fp32 distance tables of the batch, once per match ----
         TexLutParams P;
@@ -863,38 +880,12 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         P.codebook = c->d_codebook;
         P.lut = c->tex_lut.p;
         P.row_scale = c->tex_scale.p;
-        tex_lut_kernel<<<dim3(L->lt_stride, Q), 256, 0, st>>>(P);
+        tex_lut_kernel<<<dim3(L->lt_stride, Q), 256, 0, sb>>>(P);
         c->stats.kernel_launches += 1;
     }
     for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
         const int n_chunk = std::min(n_chunk_max, G - g0);
-        // ---- K1 + K2 + K3a ----
-        stamp(0);
-        {
-            TexRowmaxParams P;
-            P.lut = c->tex_lut.p;
-            P.row_scale = c->tex_scale.p;
-            P.lat_nt = D.tex_n;
-            P.lt_stride = L->lt_stride;
-            P.Q = Q;
-            P.tex_off = c->gal.tex_off;
-            P.codes = c->gal.tex_codes;
-            P.g0 = g0;
-            P.n_chunk = n_chunk;
-            const int n_rowtiles = L->lt_stride / kRowTile;
-            const int want_jobs = 4 * c->sm_count;
-            int slices = (want_jobs + Q * n_rowtiles - 1) / (Q * n_rowtiles);
-            slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
-            P.slices = slices;
-            P.rowmax_val = c->rowmax_val.p;
-            P.rowmax_j = c->rowmax_j.p;
-            P.job_counter = c->d_job_counter;
-            P.counters = c->d_slow + 4;
-            LAFIS_CUDA(c, cudaMemsetAsync(c->d_job_counter, 0, sizeof(int), st));
-            const int grid = std::min(c->sm_count, Q * n_rowtiles * slices);
-            tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, st>>>(P);
-        }
-        stamp(1);
+        begin(1, st);
         // ---- K5, then K6 + K7 ----
         {
             MinuSimParams P;
@@ -914,7 +905,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.S = c->sim.p;
             P.job_stride = job_stride;
             minu_sim_kernel<<<std::min(n_chunk, c->sm_count), kSimThreads, sim_smem, st>>>(P);
-            stamp(2);
+            end(1, st);
+            begin(2, st);
             MinuSelectParams R;
             R.slot_n = D.slot_n;
             R.lat_status = D.status;
@@ -936,7 +928,35 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
             minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
         }
-        stamp(3);
+        end(2, st);
+        // ---- texture chain (stream sb): K2 + K3a, then K3b + K4 + K9 ----
+        begin(0, sb);
+        {
+            TexRowmaxParams P;
+            P.lut = c->tex_lut.p;
+            P.row_scale = c->tex_scale.p;
+            P.lat_nt = D.tex_n;
+            P.lt_stride = L->lt_stride;
+            P.Q = Q;
+            P.tex_off = c->gal.tex_off;
+            P.codes = c->gal.tex_codes;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            const int n_rowtiles = L->lt_stride / kRowTile;
+            const int want_jobs = 4 * c->sm_count;
+            int slices = (want_jobs + Q * n_rowtiles - 1) / (Q * n_rowtiles);
+            slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
+            P.slices = slices;
+            P.rowmax_val = c->rowmax_val.p;
+            P.rowmax_j = c->rowmax_j.p;
+            P.job_counter = c->d_job_counter;
+            P.counters = c->d_slow + 4;
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_job_counter, 0, sizeof(int), sb));
+            const int grid = std::min(c->sm_count, Q * n_rowtiles * slices);
+            tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, sb>>>(P);
+        }
+        end(0, sb);
+        begin(3, st);
         // ---- K8 + K9 (minutiae) ----
         {
             GraphMinuParams P;
@@ -954,15 +974,17 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.G = G;
             P.comp = c->comp.p;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
-            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, 2 * sizeof(int), st));
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, sizeof(int), st));
             graph_minu_sparse_kernel<<<grid, SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
                 P, OverflowList{c->d_ov_count, c->ov_minu.p});
             graph_minu_dense_kernel<<<std::min<unsigned>(grid, 2u * c->sm_count), kGraphMinuThreads, kGraphMinuSmem, st>>>(
                 P, c->d_ov_count, c->ov_minu.p);
         }
-        stamp(4);
+        end(3, st);
+        begin(4, sb);
         // ---- K3b + K4 + K9 (texture) ----
         {
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count + 1, 0, sizeof(int), sb));
             GraphTexParams P;
             P.rowmax_val = c->rowmax_val.p;
             P.rowmax_j = c->rowmax_j.p;
@@ -981,19 +1003,23 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.comp = c->comp.p;
             P.slow_path_count = c->d_slow + 1;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk);
-            graph_tex_sparse_kernel<<<grid, SparseGeom<true>::NT, sizeof(SparseWork<true>), st>>>(
+            graph_tex_sparse_kernel<<<grid, SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
                 P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
-            graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, st>>>(
+            graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, sb>>>(
                 P, c->d_ov_count + 1, c->ov_tex.p);
         }
-        stamp(5);
+        end(4, sb);
         c->stats.kernel_launches += 8;
         LAFIS_CUDA(c, cudaGetLastError());
         ++chunk_id;
     }
 
+    if (c->two_streams) {  // join: the fusion needs both chains
+        LAFIS_CUDA(c, cudaEventRecord(c->ev_join, sb));
+        LAFIS_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
     // ---- K10 ----
-    stamp(0);  // chunk_id == n_chunks here: the two tail events
+    cudaEventRecord(c->stage_ev[10 * n_chunks], st);
     {
         FuseParams P;
         P.comp = c->comp.p;
@@ -1033,7 +1059,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         keys_to_hits_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(cur, nh, c->hits.p);
         c->stats.kernel_launches += 1;
     }
-    stamp(1);
+    cudaEventRecord(c->stage_ev[10 * n_chunks + 1], st);
     LAFIS_CUDA(c, cudaGetLastError());
     LAFIS_CUDA(c, cudaEventRecord(c->ev1, st));
     c->stats.pairs_scored += (uint64_t)Q * G;
@@ -1047,11 +1073,11 @@ static void collect_times(lafis_ctx* c) {
     for (int k = 0; k < c->stage_chunks; ++k)
         for (int s = 0; s < 5; ++s) {
             float t = 0;
-            cudaEventElapsedTime(&t, c->stage_ev[6 * k + s], c->stage_ev[6 * k + s + 1]);
+            cudaEventElapsedTime(&t, c->stage_ev[10 * k + 2 * s], c->stage_ev[10 * k + 2 * s + 1]);
             ms[s] += t;
         }
     float t = 0;
-    cudaEventElapsedTime(&t, c->stage_ev[6 * c->stage_chunks], c->stage_ev[6 * c->stage_chunks + 1]);
+    cudaEventElapsedTime(&t, c->stage_ev[10 * c->stage_chunks], c->stage_ev[10 * c->stage_chunks + 1]);
     ms[5] = t;
     std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
     unsigned long long cnt[8];

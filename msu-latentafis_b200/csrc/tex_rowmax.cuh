@@ -40,6 +40,7 @@ namespace lafis {
 
 constexpr int kRowTile = 16;
 constexpr int kRowmaxThreads = 512;
+constexpr int kRowmaxRegs = 96;  // leaves 16K registers per SM for the selection / graph CTAs that run beside it
 constexpr int kLutBytes = 4 * 256 * 128;  // [s][code][b][row] u16
 constexpr int kWindow = 64;               // see the bound above: 48 + 16 slack
 constexpr int kQueueCap = 480;            // candidate queue entries per warp and gallery template
@@ -139,7 +140,7 @@ __device__ __forceinline__ unsigned long long tex_best_key(float sim, int j) {
     return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)j);
 }
 
-__global__ void __launch_bounds__(kRowmaxThreads, 1) tex_rowmax_kernel(TexRowmaxParams P) {
+__global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint16_t* lut16 = reinterpret_cast<uint16_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
