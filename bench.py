@@ -311,8 +311,8 @@ def run_b200_arm(args):
     bytes_per_match = gallery_bytes / G  # this shard's 392*nRm + 24*nRt average
     nLt = int(packed.tex_off[1] - packed.tex_off[0])
     # dominant kernel: the one with the largest share of the step
-    names = ["tex_rowmax_kernel", "minu_sim_kernel", "minu_select_kernel(+slow)", "graph_minu_sparse_kernel(+dense)",
-             "graph_tex_sparse_kernel(+dense)", "fuse+topk kernels"]
+    names = ["tex_rowmax_kernel", "minu_sim_kernel", "minu_select_kernel", "graph_minu_sparse_kernel",
+             "graph_tex_sparse_kernel(+dense)", "fuse+topk kernels", "minu_select_slow_kernel", "graph_minu_dense_kernel"]
     dom = int(np.argmax(stage_ms[:6]))
     kernel_bytes = kernel_bytes_per_pair(m, G, nLt)
     dom_ms = float(stage_ms[dom])
@@ -334,7 +334,7 @@ def run_b200_arm(args):
                         "note": "nLt*nRt*16 (row, column, sub-quantizer) look-ups per pair; the fp32 formulation of "
                                 "SURVEY.md 8d is bounded by 148 SM x 32 banks x sm_max_mhz 4-byte gathers/s; this kernel "
                                 "gathers 2-byte quantised entries (smem_bandwidth_frac = bytes moved / 128 B/clk/SM)"},
-        "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:6])},
+        "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:8])},
     }
 
     cpu = None

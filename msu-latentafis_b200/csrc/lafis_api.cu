@@ -856,7 +856,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     // stage time stamps: a (start, end) pair for each of the 5 stages of a chunk, recorded on the stage's own
     // stream, and 2 for the tail
     const int n_chunks = (G + n_chunk_max - 1) / n_chunk_max;
-    while ((int)c->stage_ev.size() < 10 * n_chunks + 2) {
+    while ((int)c->stage_ev.size() < 16 * n_chunks + 2) {
         cudaEvent_t e;
         LAFIS_CUDA(c, cudaEventCreate(&e));
         c->stage_ev.push_back(e);
@@ -864,8 +864,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     c->stage_chunks = n_chunks;
     int chunk_id = 0;
     cudaStream_t sb = c->two_streams ? c->stream_b : st;
-    auto begin = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[10 * chunk_id + 2 * stage], s_); };
-    auto end = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[10 * chunk_id + 2 * stage + 1], s_); };
+    auto begin = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage], s_); };
+    auto end = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage + 1], s_); };
     if (c->two_streams) {  // the texture chain starts once the latent batch is in HBM
         LAFIS_CUDA(c, cudaEventRecord(c->ev_fork, st));
         LAFIS_CUDA(c, cudaStreamWaitEvent(sb, c->ev_fork, 0));
@@ -926,9 +926,11 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
             const unsigned jobs = (unsigned)((size_t)Q * n_chunk * 3);
             minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
+            end(2, st);
+            begin(6, st);
             minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
         }
-        end(2, st);
+        end(6, st);
         // ---- texture chain (stream sb): K2 + K3a, then K3b + K4 + K9 ----
         begin(0, sb);
         {
@@ -977,10 +979,12 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, sizeof(int), st));
             graph_minu_sparse_kernel<<<grid, SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
                 P, OverflowList{c->d_ov_count, c->ov_minu.p});
+            end(3, st);
+            begin(7, st);
             graph_minu_dense_kernel<<<std::min<unsigned>(grid, 2u * c->sm_count), kGraphMinuThreads, kGraphMinuSmem, st>>>(
                 P, c->d_ov_count, c->ov_minu.p);
         }
-        end(3, st);
+        end(7, st);
         begin(4, sb);
         // ---- K3b + K4 + K9 (texture) ----
         {
@@ -1019,7 +1023,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         LAFIS_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     // ---- K10 ----
-    cudaEventRecord(c->stage_ev[10 * n_chunks], st);
+    cudaEventRecord(c->stage_ev[16 * n_chunks], st);
     {
         FuseParams P;
         P.comp = c->comp.p;
@@ -1059,7 +1063,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         keys_to_hits_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(cur, nh, c->hits.p);
         c->stats.kernel_launches += 1;
     }
-    cudaEventRecord(c->stage_ev[10 * n_chunks + 1], st);
+    cudaEventRecord(c->stage_ev[16 * n_chunks + 1], st);
     LAFIS_CUDA(c, cudaGetLastError());
     LAFIS_CUDA(c, cudaEventRecord(c->ev1, st));
     c->stats.pairs_scored += (uint64_t)Q * G;
@@ -1071,13 +1075,14 @@ static void collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
     float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < c->stage_chunks; ++k)
-        for (int s = 0; s < 5; ++s) {
+        for (int s = 0; s < 8; ++s) {
+            if (s == 5) continue;
             float t = 0;
-            cudaEventElapsedTime(&t, c->stage_ev[10 * k + 2 * s], c->stage_ev[10 * k + 2 * s + 1]);
+            cudaEventElapsedTime(&t, c->stage_ev[16 * k + 2 * s], c->stage_ev[16 * k + 2 * s + 1]);
             ms[s] += t;
         }
     float t = 0;
-    cudaEventElapsedTime(&t, c->stage_ev[10 * c->stage_chunks], c->stage_ev[10 * c->stage_chunks + 1]);
+    cudaEventElapsedTime(&t, c->stage_ev[16 * c->stage_chunks], c->stage_ev[16 * c->stage_chunks + 1]);
     ms[5] = t;
     std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
     unsigned long long cnt[8];

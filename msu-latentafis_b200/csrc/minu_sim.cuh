@@ -32,7 +32,7 @@ namespace lafis {
 
 constexpr int kSimThreads = 512;
 constexpr int kSelThreads = 256;
-constexpr int kSelMaxCand = 384;
+constexpr int kSelMaxCand = 512;  // sorted in the histogram's 4 KB (512 x 8 B)
 constexpr int kSelBins = 1024;  // float bits >> 20 of values in (0, 1]
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -226,7 +226,7 @@ struct MinuSelectParams {
 
 __host__ __device__ inline size_t minu_select_smem_bytes(int max_nL, int max_np) {
     return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(int) * kSelBins +
-           (sizeof(uint32_t) + sizeof(int)) * kSelMaxCand + 16;
+           sizeof(int) * kSelMaxCand + 16;
 }
 
 // the reference's normalised similarity, matcher.cpp:467: float sums, "+0.000001" promotes the
@@ -240,8 +240,10 @@ __device__ __forceinline__ uint32_t exact_key(float s, float l, float r) {
 }
 // fp32 estimate of the same value; relative error < 1e-6
 __device__ __forceinline__ float approx_key(float s, float l, float r) {
-    const float den = f_sub(f_add(l, r), s);
-    return __fdividef(s, den + 0.000001f);
+    const float den = f_sub(f_add(l, r), s) + 0.000001f;
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));  // 1 ulp
+    return s * rc;
 }
 
 __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectParams P) {
@@ -263,34 +265,37 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
     float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);             // [nL]
     float* rsum = lsum + P.max_nL;                                     // [nR]
     int* hist = reinterpret_cast<int*>(rsum + P.max_np);               // [1024]
-    uint32_t* cand_key = reinterpret_cast<uint32_t*>(hist + kSelBins); // [512]
-    int* cand_e = reinterpret_cast<int*>(cand_key + kSelMaxCand);      // [512]
+    int* cand_e = reinterpret_cast<int*>(hist + kSelBins);             // [kSelMaxCand]
     __shared__ int s_ncand, s_npos, s_flag, s_bin;
     __shared__ float s_thr;
     __shared__ int s_order[kTopCorrMinu];
 
     const float* Sg = P.S + job * P.job_stride;
-    {   // S is [nL][np] with np % 4 == 0: 16-byte loads, batches of four in flight per thread
-        const float4* Sg4 = reinterpret_cast<const float4*>(Sg);
-        const int n4 = nL * (np >> 2), row4 = np >> 2;
-        for (int e0 = tid; e0 < n4; e0 += 4 * kSelThreads) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * kSelThreads;
-                v[u] = (e < n4) ? __ldcs(Sg4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * kSelThreads;
-                if (e < n4) {
-                    const int i = e / row4, c4 = e - i * row4;
-                    float* d = Ssm + i * ld + 4 * c4;
-                    d[0] = v[u].x;
-                    d[1] = v[u].y;
-                    d[2] = v[u].z;
-                    d[3] = v[u].w;
-                }
+    {   // S is [nL][np] with np % 4 == 0: a warp copies a row with 16-byte loads, two rows in flight
+        const int row4 = np >> 2;
+        for (int i = warp; i < nL; i += 2 * NW) {
+            const float4* r0 = reinterpret_cast<const float4*>(Sg + (size_t)i * np);
+            const float4* r1 = reinterpret_cast<const float4*>(Sg + (size_t)(i + NW) * np);
+            const bool has1 = i + NW < nL;
+            float4 v0a = make_float4(0.f, 0.f, 0.f, 0.f), v0b = v0a, v1a = v0a, v1b = v0a;
+            if (lane < row4) v0a = __ldcs(r0 + lane);
+            if (lane + 32 < row4) v0b = __ldcs(r0 + lane + 32);
+            if (has1 && lane < row4) v1a = __ldcs(r1 + lane);
+            if (has1 && lane + 32 < row4) v1b = __ldcs(r1 + lane + 32);
+            auto put = [&](int row, int c4, float4 v) {
+                float* d = Ssm + row * ld + 4 * c4;
+                d[0] = v.x;
+                d[1] = v.y;
+                d[2] = v.z;
+                d[3] = v.w;
+            };
+            if (lane < row4) put(i, lane, v0a);
+            if (lane + 32 < row4) put(i, lane + 32, v0b);
+            if (has1 && lane < row4) put(i + NW, lane, v1a);
+            if (has1 && lane + 32 < row4) put(i + NW, lane + 32, v1b);
+            for (int c4 = lane + 64; c4 < row4; c4 += 32) {  // templates beyond 256 minutiae
+                put(i, c4, __ldcs(r0 + c4));
+                if (has1) put(i + NW, c4, __ldcs(r1 + c4));
             }
         }
     }
@@ -324,22 +329,23 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
     // ---- pass 1: histogram of the estimates ----
     const int M = nL * nR;
     const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
-    {
-        int npos = 0;
-        for (int i = warp; i < nL; i += NW) {
-            const float l = lsum[i];
-            for (int j = lane; j < nR; j += 32) {
-                const float s = Ssm[i * ld + j];
-                if (s > 0.0f) {
-                    const float a = approx_key(s, l, rsum[j]);
-                    Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
-                    atomicAdd(&hist[min(__float_as_uint(a) >> 20, (uint32_t)(kSelBins - 1))], 1);
-                    ++npos;
-                }
+    for (int i = warp; i < nL; i += NW) {
+        const float l = lsum[i];
+        for (int j = lane; j < nR; j += 32) {
+            const float s = Ssm[i * ld + j];
+            if (s > 0.0f) {
+                const float a = approx_key(s, l, rsum[j]);
+                Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
+                atomicAdd(&hist[min(__float_as_uint(a) >> 20, (uint32_t)(kSelBins - 1))], 1);
             }
         }
-        npos = __reduce_add_sync(0xffffffffu, npos);
-        if (lane == 0) atomicAdd(&s_npos, npos);
+    }
+    __syncthreads();
+    if (warp == 0) {  // number of positive values = histogram total
+        int tot = 0;
+        for (int b = lane; b < kSelBins; b += 32) tot += hist[b];
+        tot = __reduce_add_sync(0xffffffffu, tot);
+        if (lane == 0) s_npos = tot;
     }
     __syncthreads();
     if (s_npos < K) {  // the 120th value is a zero: ties among zeros decide the order
@@ -374,19 +380,15 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
     }
     __syncthreads();
 
-    // ---- pass 2: candidates, with the reference's double-precision value ----
+    // ---- pass 2: candidates ----
     {
         const float thr = s_thr;
         for (int i = warp; i < nL; i += NW) {
-            const float l = lsum[i];
             for (int j = lane; j < nR; j += 32) {
                 const float a = Ssm[i * ld + j];  // 0 where S was not positive
                 if (a > 0.0f && a >= thr) {
                     const int pos = atomicAdd(&s_ncand, 1);
-                    if (pos < kSelMaxCand) {
-                        cand_key[pos] = exact_key(__ldg(Sg + (size_t)i * np + j), l, rsum[j]);
-                        cand_e[pos] = i * nR + j;
-                    }
+                    if (pos < kSelMaxCand) cand_e[pos] = i * nR + j;
                 }
             }
         }
@@ -397,28 +399,45 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
         if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
         return;
     }
-    // ---- K7: rank sort with the total order (value desc, index asc) ----
-    for (int c = tid; c < nc; c += kSelThreads) {
-        const uint32_t mk = cand_key[c];
-        const int me = cand_e[c];
-        int rank = 0;
-        bool tie = false;
-        for (int d = 0; d < nc; ++d) {
-            const uint32_t ok = cand_key[d];
-            const int oe = cand_e[d];
-            rank += (ok > mk) || (ok == mk && oe < me);
-            tie |= (ok == mk && d != c);
+    // ---- the reference's double-precision value (:467) of every candidate, then a bitonic sort of
+    //      (value desc, index asc) keys ----
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(hist);  // 512 keys = the histogram's 4 KB
+    int np2 = 128;
+    while (np2 < nc) np2 <<= 1;
+    __syncthreads();  // histogram no longer needed
+    for (int c = tid; c < np2; c += kSelThreads) {
+        unsigned long long k = 0ull;
+        if (c < nc) {
+            const int e = cand_e[c];
+            const int i = e / nR, j = e - i * nR;
+            const uint32_t key = exact_key(__ldg(Sg + (size_t)i * np + j), lsum[i], rsum[j]);
+            k = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);
         }
-        if (rank < K) {
-            s_order[rank] = me;
-            if (tie) s_flag = 1;
-        }
+        skey[c] = k;
     }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < np2 / 2; t += kSelThreads) {
+                const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+                const bool desc = ((lo & k) == 0);
+                const unsigned long long a = skey[lo], b = skey[hi];
+                if ((a < b) == desc) {
+                    skey[lo] = b;
+                    skey[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    // equal values among the first K (or straddling position K) make the order introsort-specific
+    if (tid < K && tid + 1 < nc && (skey[tid] >> 32) == (skey[tid + 1] >> 32)) s_flag = 1;
     __syncthreads();
     if (s_flag) {
         if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
         return;
     }
+    if (tid < K) s_order[tid] = (int)(0xffffffffu - (uint32_t)(skey[tid] & 0xffffffffull));
+    __syncthreads();
     if (tid < K) {
         const int e = s_order[tid];
         const int i = e / nR, j = e - i * nR;
@@ -430,7 +449,8 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
 
 // Jobs whose order depends on how libstdc++'s introsort permutes equal keys.
 __host__ __device__ inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np) {
-    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(uint16_t) * (size_t)max_nL * max_np + 16;
+    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) +
+           (sizeof(uint16_t) + sizeof(uint32_t)) * (size_t)max_nL * max_np + 16;
 }
 
 __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelectParams P, unsigned long long* replay_count) {
@@ -440,8 +460,8 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
     float* Ssm = reinterpret_cast<float*>(smem);
     float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);
     float* rsum = lsum + P.max_nL;
-    uint16_t* y = reinterpret_cast<uint16_t*>(rsum + P.max_np);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(Ssm);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(rsum + P.max_np);                  // dense [nL * nR]
+    uint16_t* y = reinterpret_cast<uint16_t*>(keys + (size_t)P.max_nL * P.max_np);  // [nL * nR]
     const int n_jobs = *P.slow_count;
     for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
         const size_t job = (size_t)P.slow_jobs[jb];
@@ -470,18 +490,13 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
         for (int i = warp; i < nL; i += NW)
             for (int j = lane; j < nR; j += 32) {
                 const float s = Ssm[i * ld + j];
-                keys[i * ld + j] = (s != 0.0f) ? exact_key(s, lsum[i], rsum[j]) : 0u;
+                keys[i * nR + j] = (s != 0.0f) ? exact_key(s, lsum[i], rsum[j]) : 0u;
             }
         __syncthreads();
         const int M = nL * nR;
         const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
         if (warp == 0) {  // replay of libstdc++'s introsort, warp-cooperative (stdsort_emul.h)
-            const uint32_t* kk = keys;
-            const int nRr = nR, ldd = ld;
-            auto keyfn = [kk, nRr, ldd](int e) -> uint32_t {
-                const int i = e / nRr;
-                return kk[i * ldd + (e - i * nRr)];
-            };
+            const DenseKey<uint32_t> keyfn{keys};
             warp_std_sort_desc_prefix(keyfn, y, M, K);
             if (lane == 0) atomicAdd(replay_count, 1ull);
         }
