@@ -824,8 +824,10 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     int b_double = 1;
     if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
     const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
-    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp), slow_smem = minu_select_slow_smem_bytes(maxL, maxNp);
-    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
+    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp);
+    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem / 2;
+    const size_t slow_smem = minu_select_slow_smem_bytes(maxL, maxNp, slow_dense);
+    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || sel_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
         return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE,
                     "minutiae templates of %d x %d points need %zu / %zu bytes of shared memory (limit %d)",
                     L->max_slot_n, c->max_nR, sim_smem, slow_smem, kMaxDynSmem);
@@ -918,6 +920,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             R.job_stride = job_stride;
             R.max_nL = maxL;
             R.max_np = maxNp;
+            R.slow_dense = slow_dense ? 1 : 0;
             R.corr_v = c->corr_v.p;
             R.corr_ij = c->corr_ij.p;
             R.corr_n = c->corr_n.p;

@@ -217,6 +217,7 @@ struct MinuSelectParams {
     const float* S;
     size_t job_stride;
     int max_nL, max_np;  // shared-memory geometry
+    int slow_dense;      // minu_select_slow_kernel keeps a dense copy of the keys
     float* corr_v;       // [job][120]
     uint32_t* corr_ij;   // [job][120] (i << 16) | j
     int* corr_n;         // [job]
@@ -448,9 +449,11 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
 }
 
 // Jobs whose order depends on how libstdc++'s introsort permutes equal keys.
-__host__ __device__ inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np) {
+// `dense`: a second, densely packed copy of the keys (no index arithmetic in the replay's comparator); large
+// templates that cannot afford it compare through the strided copy.
+__host__ __device__ inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np, bool dense) {
     return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) +
-           (sizeof(uint16_t) + sizeof(uint32_t)) * (size_t)max_nL * max_np + 16;
+           (sizeof(uint16_t) + (dense ? sizeof(uint32_t) : 0)) * (size_t)max_nL * max_np + 16;
 }
 
 __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelectParams P, unsigned long long* replay_count) {
@@ -460,8 +463,10 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
     float* Ssm = reinterpret_cast<float*>(smem);
     float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);
     float* rsum = lsum + P.max_nL;
-    uint32_t* keys = reinterpret_cast<uint32_t*>(rsum + P.max_np);                  // dense [nL * nR]
-    uint16_t* y = reinterpret_cast<uint16_t*>(keys + (size_t)P.max_nL * P.max_np);  // [nL * nR]
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(Ssm);                              // strided [nL][ld], in place
+    uint32_t* dkeys = reinterpret_cast<uint32_t*>(rsum + P.max_np);                  // dense [nL * nR] (slow_dense)
+    uint16_t* y = P.slow_dense ? reinterpret_cast<uint16_t*>(dkeys + (size_t)P.max_nL * P.max_np)
+                               : reinterpret_cast<uint16_t*>(dkeys);                 // [nL * nR]
     const int n_jobs = *P.slow_count;
     for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
         const size_t job = (size_t)P.slow_jobs[jb];
@@ -490,14 +495,25 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
         for (int i = warp; i < nL; i += NW)
             for (int j = lane; j < nR; j += 32) {
                 const float s = Ssm[i * ld + j];
-                keys[i * nR + j] = (s != 0.0f) ? exact_key(s, lsum[i], rsum[j]) : 0u;
+                const uint32_t key = (s != 0.0f) ? exact_key(s, lsum[i], rsum[j]) : 0u;
+                if (P.slow_dense) dkeys[i * nR + j] = key;
+                else skeys[i * ld + j] = key;
             }
         __syncthreads();
         const int M = nL * nR;
         const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
         if (warp == 0) {  // replay of libstdc++'s introsort, warp-cooperative (stdsort_emul.h)
-            const DenseKey<uint32_t> keyfn{keys};
-            warp_std_sort_desc_prefix(keyfn, y, M, K);
+            if (P.slow_dense) {
+                warp_std_sort_desc_prefix(DenseKey<uint32_t>{dkeys}, y, M, K);
+            } else {
+                const uint32_t* kk = skeys;
+                const int nRr = nR, ldd = ld;
+                auto keyfn = [kk, nRr, ldd](int e) -> uint32_t {
+                    const int i = e / nRr;
+                    return kk[i * ldd + (e - i * nRr)];
+                };
+                warp_std_sort_desc_prefix(keyfn, y, M, K);
+            }
             if (lane == 0) atomicAdd(replay_count, 1ull);
         }
         __syncthreads();

@@ -1,0 +1,118 @@
+"""GPU parity on the inputs that exercise the rare paths of the CUDA kernels: exact ties (introsort
+replays), the integer filter's overflow / unquantised rows, odd template sizes and tile shapes, batches of
+unequal latents.  Everything is compared bit for bit with the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import oracle_scores, rank_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(pkg, cb, latents, rolled, oracle, topk=5):
+    T = pkg.templates
+    m = pkg.Matcher(codebook=cb, device=0)
+    try:
+        m.set_gallery(pkg.pack_rolled(rolled))
+        out = m.match(m.latents_from_packed(pkg.pack_latents(latents)), topk=min(topk, len(rolled)), want_components=True)
+        st = m.stats()
+    finally:
+        m.close()
+    # a latent with more than 28 minutiae templates is outside the oracle's domain: the reference then fuses a
+    # never-written minutiae slot as score[28] (matcher.cpp:188), i.e. 0 - emulate with the first 28 templates
+    # and the texture component zeroed
+    trimmed = [T.FPTemplate(minu=l.minu[:28], tex=l.tex) if len(l.minu) > 28 else l for l in latents]
+    rc, comp, fin = oracle_scores(oracle, T, trimmed, rolled, cb)
+    assert (rc == 0).all()
+    for q, l in enumerate(latents):
+        if len(l.minu) > 28:
+            comp[q, :, 3] = 0.0
+            for g in range(len(rolled)):
+                fin[q, g] = oracle.lib().lo_fuse(float(comp[q, g, 0]), float(comp[q, g, 1]), float(comp[q, g, 2]), 0.0)
+    bad = np.argwhere(out["components"] != comp)
+    assert len(bad) == 0, (bad[:8], out["components"][tuple(bad[0][:2])], comp[tuple(bad[0][:2])])
+    assert np.array_equal(out["scores"], fin)
+    for q in range(len(latents)):
+        assert list(out["hits"][q]["index"]) == rank_list(fin[q], min(topk, len(rolled)))
+    return st
+
+
+def test_template_sizes_and_tile_shapes(pkg, built, golden, oracle):
+    T = pkg.templates
+    cb = golden["codebook"]
+    sizes = [(1, 1), (3, 7), (16, 16), (33, 100), (90, 600), (128, 800), (129, 810), (145, 999), (160, 1000), (161, 400),
+             (200, 300), (257, 64)]
+    raws = [T.synth_rolled_raw(3000 + k, n_minu=nm, n_tex=nt) for k, (nm, nt) in enumerate(sizes)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(80, raws[4], n_minu=37, n_tex_pts=57),     # nL not a multiple of 16, nLt = 114 < 200
+               T.synth_latent(81, raws[7], n_minu=100, n_tex_pts=208),   # nLt = 416 > 200
+               T.synth_latent(82, raws[10], n_minu=7, n_tex_pts=5)]
+    _run(pkg, cb, latents, rolled, oracle)
+
+
+def test_exact_ties_trigger_the_introsort_replays(pkg, built, golden, oracle):
+    """Duplicated gallery minutiae / latent texture points give bit-identical normalised similarities and
+    row maxima: the order std::sort leaves them in decides the candidate lists."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(3100 + k, n_minu=60, n_tex=300) for k in range(6)]
+    for r in raws:  # duplicate descriptors (different coordinates): identical columns of S
+        r.minu.des[1::2] = r.minu.des[0::2]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    lat = T.synth_latent(90, raws[2], n_minu=50, n_tex_pts=130)
+    tex = lat.tex[0]
+    tex.des[1::2] = tex.des[0::2]  # identical latent texture rows -> tied row maxima among the top 200
+    st = _run(pkg, cb, [lat], rolled, oracle)
+    assert st["minu_replays"] > 0 and st["tex_replays"] > 0, st
+
+
+def test_unquantised_rows_and_queue_overflow(pkg, built, oracle):
+    """A codebook of identical centroids makes every PQ distance-table row constant: rows whose entries are
+    all ~0 are not quantised (every column is a candidate), other rows put every column inside the filter
+    window - both overflow the candidate queue and fall back to the full exact evaluation; all similarities
+    tie, so the FIRST column must win (std::max_element)."""
+    T = pkg.templates
+    cb = np.zeros((16, 256, 6), np.float32)
+    raws = [T.synth_rolled_raw(3200 + k, n_minu=40, n_tex=120 + 30 * k) for k in range(4)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    lat = T.synth_latent(91, raws[1], n_minu=30, n_tex_pts=40)
+    lat.tex[0].des[: 20] = 0.0  # LUT rows exactly 0 -> scale 0
+    st = _run(pkg, cb, [lat], rolled, oracle)
+    assert st["tex_overflow"] > 0, st
+
+
+def test_batch_of_unequal_latents(pkg, built, golden, oracle):
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(3300 + k) for k in range(10)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(100 + q, raws[q], n_minu=20 + 13 * q, n_tex_pts=30 + 45 * q) for q in range(5)]
+    latents.append(T.synth_latent(106, raws[6], n_minu=10, n_tex_pts=20, n_minu_templates=30))  # texture unweighted
+    _run(pkg, cb, latents, rolled, oracle)
+
+
+def test_cli_binary_matches_reference_score_files(pkg, built, golden, tmp_path):
+    """The drop-in `match` executable, run the way the reference CLI is run (matching/main.cpp)."""
+    import os
+    import subprocess
+    import __graft_entry__ as entry
+    from helpers import UB_GALLERY, write_golden_files
+    T = pkg.templates
+    gdir, ldir = write_golden_files(golden, str(tmp_path))
+    cbp = str(tmp_path / "codebook.dat")
+    T.write_codebook(cbp, golden["codebook"])
+    work = tmp_path / "cwd"
+    work.mkdir()
+    sdir = str(tmp_path / "scores") + "/"
+    exe = os.path.join(entry.PKG_DIR, "bin", "match")
+    r = subprocess.run([exe, "-c", cbp, "-s", sdir, "-g", gdir, "-ldir", ldir], cwd=str(work), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for fname, text in zip(golden["n2n_files"], golden["n2n_text"]):
+        got = open(os.path.join(sdir, str(fname))).read().replace(gdir, "@G@")
+        rows = lambda s: sorted(x for x in s.strip().split("\n") if not any(u in x for u in UB_GALLERY))
+        assert rows(got) == rows(str(text)), fname
+    r = subprocess.run([exe, "-c", cbp, "-s", sdir, "-g", gdir, "-l", os.path.join(ldir, "lB.dat")], cwd=str(work),
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "Match Results" in r.stdout
+    first = open(os.path.join(sdir, "lB.csv")).read().split("\n")[1]
+    assert first.startswith('1"') and "r01_mateB.dat" in first
