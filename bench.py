@@ -292,6 +292,18 @@ def run_b200_arm(args):
         wall_e2e = (time.perf_counter() - t0) * 1e3
         ms_e2e = max(f0.elapsed_time(f1), 0.0)
 
+        # ---- per-kernel durations: two extra steps with every kernel serialised on one stream (in the timed
+        #      region the texture chain overlaps the minutiae chain, so its intervals are not exclusive) ----
+        overlapped_ms = stage_ms.copy()
+        m.set_streams(1)
+        step(L_res, False)
+        stage_acc[:] = 0
+        for _ in range(2):
+            step(L_res, False)
+        stage_ms = stage_acc / 2
+        m.set_streams(2)
+        barrier()
+
         if world > 1:
             t = torch.tensor([ms, ms_e2e, wall_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,7 +334,7 @@ def run_b200_arm(args):
     smem_peak = 148 * 32 * sm_max * 1e6
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+        "frac": achieved / hbm_peak, "traffic": ncu_traffic(names[dom], Q * G), "peak_source": peak_kind,
         "algorithmic_bytes_per_match_kernel": kernel_bytes[dom], "kernel_ms": dom_ms,
         "step": {"algorithmic_bytes_per_match": bytes_per_match, "achieved": bytes_per_match * value / 1e9,
                  "frac": bytes_per_match * value / 1e9 / hbm_peak},
@@ -335,6 +347,10 @@ def run_b200_arm(args):
                                 "SURVEY.md 8d is bounded by 148 SM x 32 banks x sm_max_mhz 4-byte gathers/s; this kernel "
                                 "gathers 2-byte quantised entries (smem_bandwidth_frac = bytes moved / 128 B/clk/SM)"},
         "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:8])},
+        "kernel_ms_note": "per-kernel CUDA-event durations from two extra steps with all kernels serialised on one stream "
+                          "(lafis_set_streams(1)); the timed region overlaps the texture chain with the minutiae chain on "
+                          "two streams, where the same intervals measure (ms): "
+                          + ", ".join(f"{n}={float(v):.1f}" for n, v in zip(names, overlapped_ms[:8])),
     }
 
     cpu = None
@@ -375,6 +391,17 @@ def run_b200_arm(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel: str, pairs: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, bytes per (latent, gallery) pair at the benchmark's sizes), scaled to this launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["bytes_per_pair"][kernel]) * pairs
+    except Exception:
+        return None
 
 
 def _as_tensor(torch, ptr: int, shape, dev):

@@ -200,6 +200,9 @@ typedef struct {
     uint64_t tex_templates;   /* ... (warp, template) visits in total */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
+/* 2 (default): the texture chain runs on a second CUDA stream concurrently with the minutiae chain;
+ * 1: every kernel on one stream, serialised - per-kernel times in lafis_stats are then exclusive. */
+LAFIS_API int lafis_set_streams(lafis_ctx* ctx, int n_streams);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */
 
 #ifdef __cplusplus

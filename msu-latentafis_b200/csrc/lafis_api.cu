@@ -319,6 +319,12 @@ const char* lafis_last_error(const lafis_ctx* c) { return c ? c->err.c_str() : g
 
 void* lafis_stream(const lafis_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+int lafis_set_streams(lafis_ctx* c, int n_streams) {
+    if (!c || n_streams < 1 || n_streams > 2) return fail(c, LAFIS_ERR_ARG, "n_streams must be 1 or 2");
+    c->two_streams = n_streams == 2;
+    return LAFIS_OK;
+}
+
 int lafis_get_stats(const lafis_ctx* c, lafis_stats* out) {
     if (!c || !out) return LAFIS_ERR_ARG;
     *out = c->stats;

@@ -74,7 +74,7 @@ EXPORTS = [
     "lafis_latents_load_files", "lafis_latents_from_packed", "lafis_latents_count", "lafis_latents_status",
     "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
-    "lafis_get_stats", "lafis_stream",
+    "lafis_get_stats", "lafis_set_streams", "lafis_stream",
 ]
 
 
@@ -124,6 +124,7 @@ def load_library():
     L.lafis_forget_gallery_dir.restype = None
     L.lafis_pq_encode.argtypes = [vp, vp, C.c_int64, vp, ci]
     L.lafis_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.lafis_set_streams.argtypes = [vp, ci]
     L.lafis_stream.argtypes = [vp]
     L.lafis_stream.restype = vp
     _lib = L
@@ -419,6 +420,10 @@ class Matcher:
                 "last_match_ms": float(s.last_match_ms), "last_stage_ms": [float(x) for x in s.last_stage_ms],
                 "minu_replays": int(s.minu_replays), "tex_replays": int(s.tex_replays), "tex_queued": int(s.tex_queued),
                 "tex_exact": int(s.tex_exact), "tex_overflow": int(s.tex_overflow), "tex_templates": int(s.tex_templates)}
+
+    def set_streams(self, n: int) -> None:
+        """2: texture chain on a second stream (default); 1: all kernels serialised on one stream."""
+        self._chk(self.L.lafis_set_streams(self.ctx, n))
 
     @property
     def stream(self) -> int:
