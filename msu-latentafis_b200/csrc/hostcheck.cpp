@@ -29,6 +29,14 @@ void hc_sort_prefix_u16(const float* key, int n, int need, int* out) {
     std_sort_desc_prefix(DenseKey<float>{key}, y.data(), n, need);
     for (int i = 0; i < std::min(n, need); ++i) out[i] = y[i];
 }
+// the same replay with every partition step resolved by the closed form the block-cooperative device version uses
+void hc_sort_prefix_closed(const float* key, int n, int need, int* out) {
+    std::vector<int> y((size_t)std::max(n, 1)), ls((size_t)std::max(n, 1)), rs((size_t)std::max(n, 1));
+    for (int i = 0; i < n; ++i) y[i] = i;
+    StdSortEmu<DenseKey<float>, int> s{DenseKey<float>{key}, y.data()};
+    s.sort_prefix(n, need, ls.data(), rs.data());
+    std::copy(y.begin(), y.begin() + std::min(n, need), out);
+}
 // libstdc++'s own answer, with the reference's comparator shape (matcher.cpp:475-476)
 void hc_std_sort(const float* key, int n, int* out) {
     std::vector<int> y((size_t)n);

@@ -831,7 +831,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
     const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
     const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp);
-    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem / 2;
+    // the dense key copy enables the block-parallel introsort replay; one CTA per SM is enough for this rare path
+    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem;
     const size_t slow_smem = minu_select_slow_smem_bytes(maxL, maxNp, slow_dense);
     if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || sel_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
         return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE,
@@ -954,10 +955,19 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.g0 = g0;
             P.n_chunk = n_chunk;
             const int n_rowtiles = L->lt_stride / kRowTile;
-            const int want_jobs = 4 * c->sm_count;
-            int slices = (want_jobs + Q * n_rowtiles - 1) / (Q * n_rowtiles);
-            slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
+            // Jobs (row tile x slice of the chunk) are drawn dynamically by one persistent CTA per SM.  With as many
+            // slices as SMs the number of equal-sized jobs is a multiple of the grid, so no CTA runs a lone extra
+            // job while the others idle (a 4.04-jobs-per-CTA split used to cost 20 % of this kernel); small chunks
+            // are cut into >= 64-template slices until there are ~4 jobs per SM.
+            int slices;
+            if (n_chunk >= 128 * c->sm_count) {
+                slices = c->sm_count;
+            } else {
+                slices = (4 * c->sm_count + Q * n_rowtiles - 1) / (Q * n_rowtiles);
+                slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
+            }
             P.slices = slices;
+            P.one = 1u;
             P.rowmax_val = c->rowmax_val.p;
             P.rowmax_j = c->rowmax_j.p;
             P.job_counter = c->d_job_counter;

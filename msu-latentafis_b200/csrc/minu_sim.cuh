@@ -8,8 +8,8 @@
 // accumulates k = 0..95 in order with an unfused fp32 multiply and add (the Eigen stand-in's order,
 // oracle/shim/Eigen/Dense).  The gallery's k-major descriptor blocks stream through a double buffer
 // with cp.async while the previous block is being multiplied; the latent's blocks stay resident
-// (single latent) or are re-staged per latent (batches).  Warp tile 16 x 128, thread tile 8 x 8: per k
-// four LDS.128 feed 64 multiply-adds.  S goes to HBM ([nL][np] per job) - ~115 KB per pair written once
+// (single latent) or are re-staged per latent (batches).  Warp tile 16 x 16*NC, thread tile 8 x NC with NC = 6..10
+// chosen per template (96..160 columns): per k four loads feed 8*NC multiply-adds.  S goes to HBM ([nL][np] per job) - ~115 KB per pair written once
 // and read once, far below what the path's fp32 issue rate lets HBM see.
 //
 // minu_select_kernel (K6 + K7).  One 256-thread CTA per (latent, template, slot), ~57 KB of shared
@@ -69,13 +69,18 @@ __host__ __device__ inline size_t minu_sim_smem_bytes(int a_slot_stride, int b_b
     return sizeof(float) * ((size_t)3 * a_slot_stride + (size_t)(b_double ? 2 : 1) * b_buf_stride);
 }
 
-// One warp tile of S = max(0, A.B^T): rows i0..i0+7 of this thread (16 per warp), columns
-// jbase + {lj*4..+3, 64+lj*4..+3} and, when WIDE, 128 + {lj*2, lj*2+1}.  k ascending, unfused.
-template <bool WIDE>
+// One warp tile of S = max(0, A.B^T): rows i0..i0+7 of this thread (16 per warp) and NC columns per thread,
+// 16 lanes across: NC = 8 is the 128-column tile (columns jbase + {lj*4..+3, 64+lj*4..+3}); the other widths
+// (96, 112, 144, 160 columns for NC = 6, 7, 9, 10) let one tile span a whole template with at most 15 padding
+// columns: 4 @ lj*4, then 4 @ 64+lj*4 (NC >= 8) or 2 @ 64+lj*2 (NC < 8), then the remaining 1 or 2 columns.
+// k ascending, unfused.
+template <int NC>
 __device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, const float* __restrict__ Bt, int npR, int lj,
                                          int jbase, int i0, int nL, float* __restrict__ out) {
-    constexpr int NC = WIDE ? 10 : 8;
-    const int ja = jbase + lj * 4, jb = ja + 64, jc = jbase + 128 + lj * 2;
+    constexpr int N2 = NC >= 8 ? 4 : 2;          // width of the second column group
+    constexpr int N3 = NC - 4 - N2;              // width of the third (0, 1 or 2)
+    constexpr int J3 = 64 + 16 * N2;             // its first column: 128 or 96
+    const int ja = jbase + lj * 4, jb = jbase + 64 + lj * N2, jc = jbase + J3 + lj * N3;
     const float* bpa = Bt + ja;
     const float* bpb = Bt + jb;
     const float* bpc = Bt + jc;
@@ -88,12 +93,25 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, 
     for (int k = 0; k < 96; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(ap + k * npL);
         const float4 a1 = *reinterpret_cast<const float4*>(ap + k * npL + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
-        const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
-        float2 b2 = make_float2(0.f, 0.f);
-        if (WIDE) b2 = *reinterpret_cast<const float2*>(bpc + k * npR);
+        float bv[NC];
+        {
+            const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
+            bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
+        }
+        if (N2 == 4) {
+            const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
+            bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
+        } else {
+            const float2 b1 = *reinterpret_cast<const float2*>(bpb + k * npR);
+            bv[4] = b1.x, bv[5] = b1.y;
+        }
+        if (N3 == 2) {
+            const float2 b2 = *reinterpret_cast<const float2*>(bpc + k * npR);
+            bv[NC - 2] = b2.x, bv[NC - 1] = b2.y;
+        } else if (N3 == 1) {
+            bv[NC - 1] = bpc[k * npR];
+        }
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -108,8 +126,16 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, 
         for (int b = 0; b < NC; ++b) v[b] = acc[a][b] < 0.0f ? 0.0f : acc[a][b];  // matcher.cpp:449-450
         float* row = out + (size_t)i * npR;
         if (ja < npR) *reinterpret_cast<float4*>(row + ja) = make_float4(v[0], v[1], v[2], v[3]);
-        if (jb < npR) *reinterpret_cast<float4*>(row + jb) = make_float4(v[4], v[5], v[6], v[7]);
-        if (WIDE && jc < npR) *reinterpret_cast<float2*>(row + jc) = make_float2(v[8], v[9]);
+        if (N2 == 4) {
+            if (jb < npR) *reinterpret_cast<float4*>(row + jb) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            if (jb < npR) *reinterpret_cast<float2*>(row + jb) = make_float2(v[4], v[5]);
+        }
+        if (N3 == 2) {
+            if (jc < npR) *reinterpret_cast<float2*>(row + jc) = make_float2(v[NC - 2], v[NC - 1]);
+        } else if (N3 == 1) {
+            if (jc < npR) row[jc] = v[NC - 1];
+        }
     }
 }
 
@@ -176,11 +202,11 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
             __syncthreads();
             if (!live) continue;
 
-            // tile list over the three slots.  A warp tile is 16 rows x 128 columns (8 x 8 per thread) or,
-            // for templates of 129..160 minutiae, 16 x 160 (8 x 10 per thread) so that one tile still
-            // spans the whole template.
-            const bool wide = nR > 128 && nR <= 160;
-            const int tiles_jj = wide ? 1 : tiles_j;
+            // tile list over the three slots.  A warp tile is 16 rows x 16*NC columns (8 x NC per thread); templates
+            // of up to 160 minutiae are spanned by ONE tile of the smallest sufficient width, larger ones by
+            // 128-column tiles.
+            const int nc = nR <= 160 ? max(6, (nR + 15) >> 4) : 8;
+            const int tiles_jj = nR <= 160 ? 1 : tiles_j;
             int t0[4];
             t0[0] = 0;
 #pragma unroll
@@ -194,8 +220,13 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
                 const int i0 = ti * 16 + li * 8;
                 const float* ap = A + (size_t)s * P.a_slot_stride + i0;
                 float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
-                if (wide) sim_tile<true>(ap, npL, Bt, npR, lj, 0, i0, nL, out);
-                else sim_tile<false>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out);
+                switch (nc) {
+                    case 6: sim_tile<6>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 7: sim_tile<7>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 9: sim_tile<9>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 10: sim_tile<10>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    default: sim_tile<8>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out); break;
+                }
             }
         }
         __syncthreads();  // everyone is done with this gallery block before it is overwritten
@@ -502,10 +533,16 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelec
         __syncthreads();
         const int M = nL * nR;
         const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
-        if (warp == 0) {  // replay of libstdc++'s introsort, warp-cooperative (stdsort_emul.h)
-            if (P.slow_dense) {
-                warp_std_sort_desc_prefix(DenseKey<uint32_t>{dkeys}, y, M, K);
-            } else {
+        if (P.slow_dense) {
+            // replay of libstdc++'s introsort with block-parallel partition steps (stdsort_emul.h); the strided copy
+            // of S is dead once the dense keys exist and serves as the two stop lists
+            __shared__ int s_part[2 * NW + 2];
+            uint16_t* Ls = reinterpret_cast<uint16_t*>(Ssm);
+            BlockStdSortEmu<DenseKey<uint32_t>, uint16_t, kSelThreads> bs{DenseKey<uint32_t>{dkeys}, y, Ls, Ls + M, s_part};
+            bs.sort_prefix(M, K);
+            if (tid == 0) atomicAdd(replay_count, 1ull);
+        } else if (warp == 0) {  // large templates: warp-cooperative replay through the strided keys
+            {
                 const uint32_t* kk = skeys;
                 const int nRr = nR, ldd = ld;
                 auto keyfn = [kk, nRr, ldd](int e) -> uint32_t {

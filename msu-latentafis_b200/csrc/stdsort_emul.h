@@ -30,6 +30,23 @@
 
 namespace lafis {
 
+// Closed form of the unguarded Hoare partition (see BlockStdSortEmu below for the derivation).  Ls: positions
+// that stop the up-scan, ascending; Rs: positions that stop the down-scan, ASCENDING (the scan meets them back to
+// front).  Returns the cut; *m_out = number of swaps, swap k exchanges Ls[k] and Rs[NR-1-k].
+template <typename IdxT>
+LAFIS_SORT_HD inline int hoare_closed_form(const IdxT* Ls, int NL, const IdxT* Rs, int NR, int last, int* m_out) {
+    int lo = 0, hi = NL < NR ? NL : NR;  // largest m with Ls[m-1] < Rs[NR-m]
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)Ls[mid - 1] < (int)Rs[NR - mid]) lo = mid;
+        else hi = mid - 1;
+    }
+    int cut = lo < NL ? (int)Ls[lo] : last;
+    if (lo > 0 && (int)Rs[NR - lo] < cut) cut = (int)Rs[NR - lo];
+    *m_out = lo;
+    return cut;
+}
+
 // KeyFn: key(index) -> comparable value.  IdxT: integer type of the index array.
 template <typename KeyFn, typename IdxT>
 struct StdSortEmu {
@@ -127,9 +144,30 @@ struct StdSortEmu {
             ++lo;
         }
     }
+    // the same step through the closed form (sequential list building; pins the formula on the CPU)
+    LAFIS_SORT_HD int partition_pivot_closed(int first, int last, IdxT* Ls, IdxT* Rs) {
+        const int mid = first + (last - first) / 2;
+        const int a = first + 1, b = mid, c = last - 1;
+        if (before(y[a], y[b])) {
+            if (before(y[b], y[c])) swp(first, b);
+            else if (before(y[a], y[c])) swp(first, c);
+            else swp(first, a);
+        } else if (before(y[a], y[c])) swp(first, a);
+        else if (before(y[b], y[c])) swp(first, c);
+        else swp(first, b);
+        int NL = 0, NR = 0;
+        for (int p = first; p < last; ++p) {
+            if (p > first && !before(y[p], y[first])) Ls[NL++] = (IdxT)p;
+            if (!before(y[first], y[p])) Rs[NR++] = (IdxT)p;
+        }
+        int m;
+        const int cut = hoare_closed_form(Ls, NL, Rs, NR, last, &m);
+        for (int k = 0; k < m; ++k) swp((int)Ls[k], (int)Rs[NR - 1 - k]);
+        return cut;
+    }
     // y must hold 0..n-1 on entry (std::iota).  On return positions [0, min(need, n)) are what
     // std::sort leaves there; later positions are unspecified.
-    LAFIS_SORT_HD void sort_prefix(int n, int need) {
+    LAFIS_SORT_HD void sort_prefix(int n, int need, IdxT* Ls = nullptr, IdxT* Rs = nullptr) {
         if (n <= 0) return;
         if (need > n) need = n;
         int lg = 0;
@@ -152,7 +190,7 @@ struct StdSortEmu {
                     break;
                 }
                 --f.depth;
-                const int cut = partition_pivot(f.first, f.last);
+                const int cut = Ls ? partition_pivot_closed(f.first, f.last, Ls, Rs) : partition_pivot(f.first, f.last);
                 if (cut < need) stack[sp++] = Frame{cut, f.last, f.depth};  // the recursive call
                 f.last = cut;                                                // the loop's continuation
             }
@@ -307,6 +345,148 @@ __device__ inline void warp_std_sort_desc_prefix(KeyFn key, IdxT* y, int n, int 
     WarpStdSortEmu<KeyFn, IdxT> s{key, y, lane};
     s.sort_prefix(n, need);
 }
+
+// Block-cooperative replay for large index sets (the 9,600 normalised similarities of a minutiae match).
+// With random keys each scanning loop of the Hoare partition stops after ~2 elements, so the warp version
+// above spends its time on ~n/4 sequential swaps.  The partition's outcome has a closed form:
+//   L = positions p in (first, last) where the up-scan stops,   key(y[p]) <= key(pivot), ascending;
+//   R = positions p in [first, last) where the down-scan stops, key(y[p]) >= key(pivot), descending
+//       (position `first` holds the pivot and always stops the down-scan).
+// Until the scans cross they only ever read positions the earlier swaps have not touched, so swap k pairs
+// L[k] with R[k] exactly while L[k] < R[k] (a prefix property: L ascends, R descends).  After the m swaps
+// that happen, the up-scan continues over untouched positions until L[m] or until R[m-1], which now holds
+// a value that stops it; the down-scan likewise ends at max(R[m], L[m-1]) <= that position, so the loop
+// returns cut = min(L[m], R[m-1]).  Both lists come from one ballot/prefix-sum pass over the segment and
+// the m swaps are independent: O(n / NT) per partition instead of O(n).
+// `Ls` / `Rs`: scratch of n entries each; `sh`: 2 * NT/32 + 2 ints; all in shared memory.  Every thread of
+// the block calls with the same arguments.
+template <typename KeyFn, typename IdxT, int NT>
+struct BlockStdSortEmu {
+    static constexpr int NW = NT / 32;
+    KeyFn key;
+    IdxT* y;
+    IdxT* Ls;
+    IdxT* Rs;
+    int* sh;
+
+    __device__ int partition_pivot(int first, int last) {
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        if (tid == 0) {
+            StdSortEmu<KeyFn, IdxT> seq{key, y};
+            const int mid = first + (last - first) / 2;
+            const int a = first + 1, b = mid, c = last - 1;
+            if (seq.before(y[a], y[b])) {
+                if (seq.before(y[b], y[c])) seq.swp(first, b);
+                else if (seq.before(y[a], y[c])) seq.swp(first, c);
+                else seq.swp(first, a);
+            } else if (seq.before(y[a], y[c])) seq.swp(first, a);
+            else if (seq.before(y[b], y[c])) seq.swp(first, c);
+            else seq.swp(first, b);
+        }
+        __syncthreads();
+        const auto pk = key((int)y[first]);
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int baseL = 0, baseR = 0;
+        for (int p0 = first; p0 < last; p0 += NT) {
+            const int p = p0 + tid;
+            bool isL = false, isR = false;
+            if (p < last) {
+                const auto kp = key((int)y[p]);
+                isL = p > first && !(kp > pk);
+                isR = !(pk > kp);
+            }
+            const unsigned mL = __ballot_sync(0xffffffffu, isL), mR = __ballot_sync(0xffffffffu, isR);
+            if (lane == 0) {
+                sh[warp] = __popc(mL);
+                sh[NW + warp] = __popc(mR);
+            }
+            __syncthreads();
+            int offL = baseL, offR = baseR;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int cL = sh[w], cR = sh[NW + w];
+                if (w < warp) {
+                    offL += cL;
+                    offR += cR;
+                }
+                baseL += cL;
+                baseR += cR;
+            }
+            if (isL) Ls[offL + __popc(mL & lt_mask)] = (IdxT)p;
+            if (isR) Rs[offR + __popc(mR & lt_mask)] = (IdxT)p;  // ascending here, read back to front
+            __syncthreads();
+        }
+        const int NL = baseL, NR = baseR;
+        if (tid == 0) {
+            int m0;
+            sh[2 * NW + 1] = hoare_closed_form(Ls, NL, Rs, NR, last, &m0);
+            sh[2 * NW] = m0;
+        }
+        __syncthreads();
+        const int m = sh[2 * NW], cut = sh[2 * NW + 1];
+        for (int k = tid; k < m; k += NT) {
+            const int a = Ls[k], b = Rs[NR - 1 - k];
+            const IdxT t = y[a];
+            y[a] = y[b];
+            y[b] = t;
+        }
+        __syncthreads();
+        return cut;
+    }
+
+    __device__ void sort_prefix(int n, int need) {
+        const int tid = threadIdx.x;
+        for (int i = tid; i < n; i += NT) y[i] = (IdxT)i;
+        __syncthreads();
+        if (n <= 0) return;
+        if (need > n) need = n;
+        int lg = 0;
+        for (int m = n; m > 1; m >>= 1) ++lg;
+        StdSortEmu<KeyFn, IdxT> seq{key, y};  // small ranges, heap sort, insertion sort: thread 0 only
+        struct Frame {
+            int first, last, depth;
+        };
+        Frame stack[72];
+        int sp = 0, done_to = 0;
+        stack[sp++] = Frame{0, n, 2 * lg};
+        while (sp > 0) {
+            Frame f = stack[--sp];
+            if (f.first >= need) continue;
+            while (f.last - f.first > 16) {
+                if (f.depth == 0) {
+                    if (tid == 0) seq.heap_sort(f.first, f.last);
+                    __syncthreads();
+                    break;
+                }
+                --f.depth;
+                int cut;
+                if (f.last - f.first > 96) {
+                    cut = partition_pivot(f.first, f.last);
+                } else {
+                    if (tid == 0) sh[2 * NW + 1] = seq.partition_pivot(f.first, f.last);
+                    __syncthreads();
+                    cut = sh[2 * NW + 1];
+                    __syncthreads();
+                }
+                if (cut < need) stack[sp++] = Frame{cut, f.last, f.depth};
+                f.last = cut;
+            }
+            if (f.last > done_to) done_to = f.last;
+        }
+        if (tid == 0) {
+            if (n > 16) {
+                int E = done_to;
+                if (E < 16) E = 16;
+                if (E > n) E = n;
+                seq.insertion_sort(0, 16);
+                for (int i = 16; i < E; ++i) seq.unguarded_linear_insert(i);
+            } else {
+                seq.insertion_sort(0, n);
+            }
+        }
+        __syncthreads();
+    }
+};
 #endif
 
 }  // namespace lafis

@@ -9,48 +9,58 @@
 // fp32:
 //
 //  tex_lut_kernel        K1 verbatim (fp32, k ascending, unfused) into HBM, LUT[q][row][m][code], plus a
-//                        per-row scale = 4095 / max entry.
-//  tex_rowmax_kernel     A persistent CTA owns 16 latent rows.  It keeps a 12-BIT QUANTISED copy of their
+//                        per-row scale = 255 / max entry.
+//  tex_rowmax_kernel     A persistent CTA owns 32 latent rows.  It keeps an 8-BIT QUANTISED copy of their
 //                        LUT rows in 128 KB of shared memory, [s][code][b][row] (sub-quantizer m = 4s + b),
 //                        and streams the gallery's PQ code words through it: one LDS.128 returns the
-//                        quantised entries of 8 rows, which are summed as packed 16-bit integers (16
-//                        entries of <= 4095 cannot overflow 16 bits).  With q = floor(LUT * scale) computed
-//                        in fp32, q - 1 < LUT * scale < q + 2, so for the integer sums
-//                        Dq - 16 < scale * D < Dq + 32: a column whose Dq exceeds the row's minimum Dq by
-//                        more than 48 (+ slack for the fp32 rounding of the reference's own summation;
-//                        kWindow = 64 in total) has a strictly smaller similarity than the column holding
-//                        that minimum and can neither be the maximum nor tie with it.  Columns inside the
-//                        window (typically 1-3 per row) are queued and re-evaluated EXACTLY - fp32 LUT from
-//                        HBM/L2, the reference's four running values and summation order - and the row
-//                        maximum / first arg-max is taken over those exact values.
+//                        quantised entries of 16 rows (4 words x 4 bytes).  Sixteen such words are summed
+//                        per column without unpacking: `all` = plain 32-bit sum of the words (carries run
+//                        into the neighbouring byte lanes) and `odd` = sum of the words' odd bytes spread to
+//                        16-bit fields; then  odd  holds the sums of rows 1|3 and  all - (odd << 8)  those of
+//                        rows 0|2, each below 2^12.  With q = rint(LUT * scale) in fp32,
+//                        |q - LUT*scale| < 0.5001, so for the integer sums |Dq - scale*D| < 8.001: a column
+//                        whose Dq exceeds the row's minimum Dq by more than 16 (+ < 0.4 for the fp32
+//                        rounding of the reference's own summation; kWindow = 18 in total) has a strictly
+//                        smaller similarity than the column holding that minimum and can neither be the
+//                        maximum nor tie with it.
+//                        The stream loop is branch-free: per (lane, row) it tracks, as packed 16-bit fields
+//                        (Dq >> 2) << 6 | batch, the three smallest of the lane's columns (a lane sees every
+//                        16th column; the batch index names the column).  After the template, the row
+//                        minimum is a warp reduction; every lane whose best column is inside the window
+//                        contributes its best and second best column as candidates; a lane whose THIRD best
+//                        is inside the window too (< 1 % of the rows) has its ~50 columns re-scanned.  The
+//                        candidates (~1.9 per row) are re-evaluated EXACTLY - fp32 LUT from L2, the
+//                        reference's four running values and summation order - and the row maximum /
+//                        first arg-max is taken over those exact values.
 //
-// The quantised pass moves half the shared-memory bytes per (row, column, sub-quantizer) of an fp32 pass,
-// which is the resource that bounds this path; the exact pass touches < 1 % of the
-// entries.  Shared-memory gather layout as before: lanes of a pair share the rolled point
-// j = 16*batch + 4*quarter + pair and split the 16 rows 8|8; at step t of group s, pair p gathers
-// sub-quantizer m = 4s + ((t+p)&3), so the four pairs of an LDS.128 phase hit the four 32-byte b-slices of
-// one 128-byte line: conflict-free.
+// The quantised pass moves a quarter of the shared-memory bytes per (row, column, sub-quantizer) of an fp32
+// pass, which is the resource that bounds this path.  Shared-memory gather layout: lanes
+// of a pair share the rolled point j = 16*batch + 4*quarter + pair and split the 32 rows 16|16; at step t
+// of group s, pair p gathers sub-quantizer m = 4s + ((t+p)&3), so the four pairs of an LDS.128 phase hit
+// the four 32-byte b-slices of one 128-byte line: conflict-free.
 //
-// Degenerate rows (all LUT entries ~0) get scale 0: every column is then inside the window and the row is
-// evaluated exactly in full, like a template whose candidate queue overflows.
+// Degenerate rows (all LUT entries ~0) get scale 0 and are evaluated exactly in full, like the rows of a
+// template whose candidate list overflows.
 #pragma once
 #include "device_common.cuh"
 
 namespace lafis {
 
-constexpr int kRowTile = 16;
+constexpr int kRowTile = 32;
 constexpr int kRowmaxThreads = 512;
 constexpr int kRowmaxRegs = 96;  // leaves 16K registers per SM for the selection / graph CTAs that run beside it
-constexpr int kLutBytes = 4 * 256 * 128;  // [s][code][b][row] u16
-constexpr int kWindow = 64;               // see the bound above: 48 + 16 slack
-constexpr int kQueueCap = 480;            // candidate queue entries per warp and gallery template
-constexpr int kQLevels = 4095;
+constexpr int kLutBytes = 4 * 256 * 128;  // [s][code][b][row] u8
+constexpr int kWindow = 18;               // see the bound above: 16.002 + 0.4, rounded up with slack
+constexpr int kWindowQ = (kWindow + 3) / 4 + 1;  // the same window on distances tracked as Dq >> 2: floor((x + W) / 4) <= floor(x / 4) + ceil(W / 4) + 1
+constexpr int kCandCap = 192;             // exact re-evaluations per warp and gallery template
+constexpr int kAmbCap = 32;               // (lane, row) re-scans per warp and gallery template
+constexpr int kQLevels = 255;
 
 struct TexWarpState {
     unsigned long long best[kRowTile];  // (sortable similarity << 32) | ~column: max = largest value, first column
-    uint32_t rmin[kRowTile];            // running minimum of the quantised distance per row
-    uint32_t queue[kQueueCap];          // row | column << 4 | Dq << 14
-    int count, overflow;
+    uint32_t cand[kCandCap];            // row | column << 5
+    uint32_t amb[kAmbCap];              // row | lane << 5 | limit << 10
+    uint32_t full_rows;                 // rows that need every column evaluated exactly
 };
 constexpr int kRowmaxSmem = kLutBytes + (kRowmaxThreads / 32) * (int)sizeof(TexWarpState);
 
@@ -114,10 +124,11 @@ struct TexRowmaxParams {
     const uint4* codes;
     int g0, n_chunk;           // gallery templates [g0, g0+n_chunk)
     int slices;                // the chunk is cut into this many slices
+    uint32_t one;              // = 1, opaque to the compiler: x * one + y keeps an addition on the FMA pipe (IMAD)
     float* rowmax_val;         // [Q][n_chunk][lt_stride]
     uint16_t* rowmax_j;        // [Q][n_chunk][lt_stride]
     int* job_counter;          // zeroed before launch
-    unsigned long long* counters;  // [4] statistics: queued, exact evaluations, overflowed templates, templates
+    unsigned long long* counters;  // [4] statistics: candidates, exact evaluations, overflowed templates, templates
 };
 
 __device__ __forceinline__ float tex_exact_sim(const float* __restrict__ lut_row, uint4 c) {
@@ -140,34 +151,58 @@ __device__ __forceinline__ unsigned long long tex_best_key(float sim, int j) {
     return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)j);
 }
 
+// row (0..15 within the lane's half of the tile) held by 16-bit field f of the packed sums:
+// words 0,2,4,6 = all - (odd << 8) of LDS word w = f >> 2 (rows 4w | 4w+2), words 1,3,5,7 = odd (rows 4w+1 | 4w+3)
+__device__ __forceinline__ constexpr int tex_field_row(int f) { return 4 * (f >> 2) + ((f >> 1) & 1) + 2 * (f & 1); }
+
+// quantised distance of ONE row to one rolled point (the re-scan of an ambiguous lane)
+__device__ __forceinline__ uint32_t tex_quant_dist(const unsigned char* __restrict__ lut8, int row, uint4 c) {
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    uint32_t d = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t code = (w[s] >> (8 * b)) & 0xffu;
+            d += lut8[((s * 256 + code) * 4 + b) * kRowTile + row];
+        }
+    return d;
+}
+
 __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint16_t* lut16 = reinterpret_cast<uint16_t*>(smem);
+    unsigned char* lut8 = smem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kRowmaxThreads / 32;
     TexWarpState& ws = reinterpret_cast<TexWarpState*>(smem + kLutBytes)[warp];
-    __shared__ int s_job;
+    __shared__ int s_job, s_next;
     __shared__ float s_scale[kRowTile];
 
-    const int n_rowtiles = P.lt_stride / kRowTile;
+    const int n_rowtiles = (P.lt_stride + kRowTile - 1) / kRowTile;
     const int n_jobs = P.Q * n_rowtiles * P.slices;
     const int slice_len = (P.n_chunk + P.slices - 1) / P.slices;
 
     // lane roles
     const int pr = (lane >> 1) & 3, hf = lane & 1;
     const int jl = (lane >> 3) * 4 + pr;  // rolled point within a batch of 16
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned hf_mask = hf ? 0xaaaaaaaau : 0x55555555u;
     uint32_t sel[4], off[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int b = (t + pr) & 3;
         sel[t] = 0x4440u | (uint32_t)b;  // __byte_perm selector: byte b of the word, zero extended
-        off[t] = smem_u32(lut16) + (uint32_t)(b * 32 + hf * 16);
+        off[t] = smem_u32(lut8) + (uint32_t)(b * 32 + hf * 16);
     }
-    unsigned long long n_queued = 0, n_exact = 0, n_over = 0, n_tpl = 0;
+    unsigned long long n_cand = 0, n_exact = 0, n_over = 0, n_tpl = 0;
+    const uint32_t one = P.one;
 
     for (;;) {
         __syncthreads();  // previous job's LUT no longer in use
-        if (tid == 0) s_job = atomicAdd(P.job_counter, 1);
+        if (tid == 0) {
+            s_job = atomicAdd(P.job_counter, 1);
+            s_next = 0;
+        }
         __syncthreads();
         const int job = s_job;
         if (job >= n_jobs) break;
@@ -177,43 +212,66 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
         const int nLt = P.lat_nt[q];
         if (rt * kRowTile >= nLt) continue;  // uniform across the CTA
 
-        // ---- quantised LUT of rows [rt*16, rt*16+16) ----
+        // ---- quantised LUT of rows [rt*32, rt*32+32) ----
         const size_t row0 = (size_t)q * P.lt_stride + (size_t)rt * kRowTile;
-        if (tid < kRowTile) s_scale[tid] = P.row_scale[row0 + tid];
+        if (tid < kRowTile) s_scale[tid] = (rt * kRowTile + tid < P.lt_stride) ? P.row_scale[row0 + tid] : -1.0f;
         __syncthreads();
-        for (int r = 0; r < kRowTile; ++r) {
-            const float sc = s_scale[r];
-            const float* src = P.lut + (row0 + r) * 4096;
-            for (int mc = tid; mc < 4096; mc += kRowmaxThreads) {
-                const int m = mc >> 8, code = mc & 255;
+        // a thread quantises 16 rows of one (sub-quantizer, code) and stores them as one 16-byte vector
+        for (int e = tid; e < 2 * 4096; e += kRowmaxThreads) {
+            const int mc = e & 4095, half = e >> 12;
+            const int m = mc >> 8, code = mc & 255;
+            uint32_t wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const float sc = s_scale[half * 16 + r];
                 uint32_t qv = 0;
-                if (sc > 0.0f) qv = (uint32_t)min((int)floorf(__ldg(src + mc) * sc), kQLevels);
-                lut16[(((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + r] = (uint16_t)qv;
+                if (sc > 0.0f) qv = (uint32_t)min((int)rintf(f_mul(__ldg(P.lut + (row0 + half * 16 + r) * 4096 + mc), sc)), kQLevels);
+                wv[r >> 2] |= qv << (8 * (r & 3));
             }
+            *reinterpret_cast<uint4*>(lut8 + (((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + half * 16) =
+                make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
         __syncthreads();
-        // rows this lane accumulates: hf*8 .. hf*8+7; padding rows never produce candidates
-        uint32_t row_live = 0;
+        // rows of this lane's half: live (take part), degenerate (scale 0: every column is a candidate)
+        uint32_t row_live = 0, row_degen = 0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (s_scale[hf * 8 + r] >= 0.0f) row_live |= 1u << r;
+        for (int r = 0; r < 16; ++r) {
+            const float sc = s_scale[hf * 16 + r];
+            if (sc > 0.0f) row_live |= 1u << r;
+            if (sc == 0.0f) row_degen |= 1u << r;
+        }
+        const uint32_t degen_all = __shfl_sync(0xffffffffu, row_degen, 0) | (__shfl_sync(0xffffffffu, row_degen, 1) << 16);
 
-        // ---- stream the slice ----
+        // ---- stream the slice: warps draw templates from a shared counter (template sizes vary 600..1000 points) ----
         const int t_begin = slice * slice_len;
         const int t_end = min(P.n_chunk, t_begin + slice_len);
-        for (int tl = t_begin + warp; tl < t_end; tl += NW) {
+        for (;;) {
+            int tl = 0;
+            if (lane == 0) tl = t_begin + atomicAdd(&s_next, 1);
+            tl = __shfl_sync(0xffffffffu, tl, 0);
+            if (tl >= t_end) break;
             const int g = P.g0 + tl;
             const uint32_t base = P.tex_off[g];
             const int n = (int)(P.tex_off[g + 1] - base);
             if (n <= 0) continue;
             ++n_tpl;
-            if (lane < kRowTile) ws.best[lane] = 0ull;
-            __syncwarp();
+            ws.best[lane] = 0ull;
             const uint4* cp = P.codes + base + jl;
 
-            // quantised distances of my 8 rows to the point of batch j0
-            auto batch = [&](uint4 c, uint32_t* dq) {
-                uint32_t acc[4] = {0u, 0u, 0u, 0u};
+            // per (lane, row): the two smallest tracking fields of this lane's columns, as packed 16-bit fields
+            // (Dq >> 2) << 6 | batch: 10 bits of distance (Dq <= 4080), 6 bits of batch index (<= 62)
+            uint32_t f1[8], f2[8], f3[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f1[u] = f2[u] = f3[u] = 0xffffffffu;
+
+            uint4 cnext = __ldg(cp);
+            uint32_t bp = 0;  // batch index in both fields
+            for (int j0 = 0; j0 < n; j0 += 16, bp += 0x00010001u) {
+                const uint4 c = cnext;
+                if (j0 + 16 < n) cnext = __ldg(cp + j0 + 16);
+                // The integer ALU pipe (PRMT, IADD3, VIMNMX: 16 lanes/clk per scheduler) would bound this loop, so the
+                // additions go to the FMA pipe (IMAD with a run-time multiplier of 1); the two pipes end up level.
+                uint32_t all[4] = {0u, 0u, 0u, 0u}, odd[4] = {0u, 0u, 0u, 0u};
                 const uint32_t words[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
@@ -221,111 +279,119 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                     for (int t = 0; t < 4; ++t) {
                         const uint32_t code = __byte_perm(words[s], 0u, sel[t]);
                         const uint32_t addr = off[t] + code * 128u + (uint32_t)(s * 32768);
-                        uint32_t v0, v1, v2, v3;
+                        uint32_t v[4];
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                                      : "r"(addr));
-                        acc[0] += v0;  // packed 16-bit sums: 16 entries of <= 4095 stay below 2^16
-                        acc[1] += v1;
-                        acc[2] += v2;
-                        acc[3] += v3;
-                    }
-                }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    dq[2 * r] = acc[r] & 0xffffu;
-                    dq[2 * r + 1] = acc[r] >> 16;
-                }
-            };
-
-            // Per-row thresholds live in registers and are refreshed from the warp's shared minima every four
-            // batches.  A threshold is (smallest Dq seen so far) + kWindow, so a stale value is only ever
-            // too large: it can queue too much, never miss a candidate.
-            const unsigned hf_mask = hf ? 0xaaaaaaaau : 0x55555555u;
-            uint32_t thr[8];
-            {   // warm-up: minima over the first 32 points, nothing queued
-                uint32_t lmin[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) lmin[r] = 0xffffu;
-                for (int j0 = 0; j0 < n && j0 < 32; j0 += 16) {
-                    uint32_t dq[8];
-                    batch(__ldg(cp + j0), dq);
-                    if (j0 + jl < n) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) lmin[r] = min(lmin[r], dq[r]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint32_t mn = __reduce_min_sync(hf_mask, lmin[r]);
-                    thr[r] = mn + kWindow;
-                    if (lane < 2) ws.rmin[hf * 8 + r] = mn;  // lanes 0 / 1 publish rows 0..7 / 8..15
-                }
-            }
-            if (lane == 0) ws.count = 0;
-            __syncwarp();
-            uint4 cnext = __ldg(cp);
-            int since_refresh = 0;
-            for (int j0 = 0; j0 < n; j0 += 16) {
-                const uint4 c = cnext;
-                if (j0 + 16 < n) cnext = __ldg(cp + j0 + 16);
-                uint32_t dq[8];
-                batch(c, dq);
-                const int j = j0 + jl;
-                if (j < n) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (dq[r] <= thr[r] && ((row_live >> r) & 1u)) {  // rare: ~6 per row and template
-                            const int slot = atomicAdd(&ws.count, 1);
-                            if (slot < kQueueCap) ws.queue[slot] = (uint32_t)(hf * 8 + r) | ((uint32_t)j << 4) | (dq[r] << 14);
-                            if (dq[r] + kWindow < thr[r]) {  // a new minimum: share it through shared memory
-                                thr[r] = dq[r] + kWindow;
-                                atomicMin(&ws.rmin[hf * 8 + r], dq[r]);
-                            }
+                        for (int w = 0; w < 4; ++w) {
+                            all[w] = v[w] * one + all[w];                  // bytes carry into their neighbours: resolved below
+                            const uint32_t o = __byte_perm(v[w], 0u, 0x4341u);  // rows 1 | 3 as 16-bit fields
+                            if (s == 3) odd[w] += o;  // a quarter stays on the ALU pipe (pairs fuse into IADD3)
+                            else odd[w] = o * one + odd[w];
                         }
                     }
                 }
-                if (++since_refresh == 4) {  // pick up minima found by the other lanes
-                    since_refresh = 0;
+                if (j0 + jl < n) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) thr[r] = min(thr[r], ws.rmin[hf * 8 + r] + kWindow);
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t dq[2] = {all[w] - (odd[w] << 8), odd[w]};  // rows 4w | 4w+2, rows 4w+1 | 4w+3
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int u = 2 * w + h;
+                            const uint32_t t = ((dq[h] << 4) & 0xffc0ffc0u) | bp;
+                            f3[u] = __vminu2(f3[u], __vmaxu2(f2[u], t));
+                            f2[u] = __vminu2(f2[u], __vmaxu2(f1[u], t));
+                            f1[u] = __vminu2(f1[u], t);
+                        }
+                    }
                 }
             }
-            __syncwarp();
-            // queue state
-            if (lane == 0) {
-                const int count = ws.count;
-                ws.overflow = count > kQueueCap;
-                ws.count = min(count, kQueueCap);
+
+            // ---- candidates: columns whose quantised distance is within kWindow of the row minimum ----
+            int cnt = 0, acnt = 0;
+#pragma unroll
+            for (int f = 0; f < 16; ++f) {
+                const int rl = tex_field_row(f);
+                const uint32_t mine = (f & 1) ? (f1[f >> 1] >> 16) : (f1[f >> 1] & 0xffffu);
+                const uint32_t second = (f & 1) ? (f2[f >> 1] >> 16) : (f2[f >> 1] & 0xffffu);
+                const uint32_t third = (f & 1) ? (f3[f >> 1] >> 16) : (f3[f >> 1] & 0xffffu);
+                // Dq_j <= Dq_min + kWindow  =>  (Dq_j >> 2) <= (Dq_min >> 2) + kWindowQ
+                const uint32_t limq = (__reduce_min_sync(hf_mask, mine) >> 6) + kWindowQ;
+                const bool live = (row_live >> rl) & 1u;
+                const bool amb = live && (third >> 6) <= limq;                 // >= 3 of my columns inside the window: re-scan
+                const bool cand = live && !amb && (mine >> 6) <= limq;         // my best column
+                const bool cand2 = cand && (second >> 6) <= limq;              // and my second best
+                const unsigned mc = __ballot_sync(0xffffffffu, cand), mc2 = __ballot_sync(0xffffffffu, cand2);
+                const unsigned ma = __ballot_sync(0xffffffffu, amb);
+                const int row = hf * 16 + rl;
+                if (cand) {
+                    const int pos = cnt + __popc(mc & lt_mask);
+                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(16 * (int)(mine & 63u) + jl) << 5);
+                }
+                cnt += __popc(mc);
+                if (cand2) {
+                    const int pos = cnt + __popc(mc2 & lt_mask);
+                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(16 * (int)(second & 63u) + jl) << 5);
+                }
+                cnt += __popc(mc2);
+                if (amb) {
+                    const int pos = acnt + __popc(ma & lt_mask);
+                    if (pos < kAmbCap) ws.amb[pos] = (uint32_t)row | ((uint32_t)lane << 5) | (limq << 10);
+                }
+                acnt += __popc(ma);
             }
+            __syncwarp();
+            bool overflow = acnt > kAmbCap;
+            // re-scan of the ambiguous (lane, row)s: all 32 lanes share the ~n/16 columns of that lane
+            for (int a = 0; a < acnt && !overflow; ++a) {
+                const uint32_t ent = ws.amb[a];
+                const int row = (int)(ent & 31u), al = (int)((ent >> 5) & 31u);
+                const uint32_t lim = ent >> 10;
+                const int ajl = (al >> 3) * 4 + ((al >> 1) & 3);
+                for (int b0 = 0; b0 * 16 < n; b0 += 32) {
+                    const int j = (b0 + lane) * 16 + ajl;
+                    bool hit = false;
+                    if (j < n) hit = (tex_quant_dist(lut8, row, __ldg(P.codes + base + j)) >> 2) <= lim;
+                    const unsigned mh = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int pos = cnt + __popc(mh & lt_mask);
+                        if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)j << 5);
+                    }
+                    cnt += __popc(mh);
+                }
+            }
+            overflow = overflow || cnt > kCandCap;
             __syncwarp();
 
             // ---- exact re-evaluation of the candidates ----
             const float* lut_rows = P.lut + row0 * 4096;
-            if (ws.overflow) {
+            uint32_t full = degen_all;  // rows evaluated in full
+            if (overflow) {
                 ++n_over;
-                for (int e = lane; e < kRowTile * n; e += 32) {
-                    const int r = e / n, j = e - r * n;
-                    if (s_scale[r] < 0.0f) continue;
+                full = 0xffffffffu;
+            } else {
+                n_cand += (lane == 0) ? cnt : 0;
+                for (int e = lane; e < cnt; e += 32) {
+                    const uint32_t ent = ws.cand[e];
+                    const int r = (int)(ent & 31u), j = (int)(ent >> 5);
                     const float sim = tex_exact_sim(lut_rows + (size_t)r * 4096, __ldg(P.codes + base + j));
                     atomicMax(&ws.best[r], tex_best_key(sim, j));
                     ++n_exact;
                 }
-            } else {
-                const int cnt = ws.count;
-                n_queued += (lane == 0) ? cnt : 0;
-                for (int e = lane; e < cnt; e += 32) {
-                    const uint32_t ent = ws.queue[e];
-                    const int r = (int)(ent & 15u), j = (int)((ent >> 4) & 1023u);
-                    const uint32_t dqv = ent >> 14;
-                    if (dqv > ws.rmin[r] + kWindow) continue;  // outside the final window
+            }
+            while (full) {  // rare: degenerate rows / overflowed templates
+                const int r = __ffs(full) - 1;
+                full &= full - 1;
+                if (s_scale[r] < 0.0f) continue;
+                for (int j = lane; j < n; j += 32) {
                     const float sim = tex_exact_sim(lut_rows + (size_t)r * 4096, __ldg(P.codes + base + j));
                     atomicMax(&ws.best[r], tex_best_key(sim, j));
                     ++n_exact;
                 }
             }
             __syncwarp();
-            if (lane < kRowTile && s_scale[lane] >= 0.0f) {
+            if (s_scale[lane] >= 0.0f) {
                 const unsigned long long k = ws.best[lane];
                 uint32_t u = (uint32_t)(k >> 32);
                 u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
@@ -339,7 +405,7 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
     // statistics, one atomic per warp
     n_exact = __reduce_add_sync(0xffffffffu, (unsigned)n_exact);
     if (lane == 0) {
-        atomicAdd(P.counters + 0, n_queued);
+        atomicAdd(P.counters + 0, n_cand);
         atomicAdd(P.counters + 1, n_exact);
         atomicAdd(P.counters + 2, n_over);
         atomicAdd(P.counters + 3, n_tpl);

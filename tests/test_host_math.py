@@ -62,6 +62,9 @@ def test_sort_prefix_equals_std_sort(hc, n):
             got = np.zeros(need, np.int32)
             hc.hc_sort_prefix(key.ctypes.data_as(C.c_void_p), n, need, got.ctypes.data_as(C.c_void_p))
             assert np.array_equal(got, full[:need]), (n, levels, need)
+            gotc = np.zeros(need, np.int32)
+            hc.hc_sort_prefix_closed(key.ctypes.data_as(C.c_void_p), n, need, gotc.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(gotc, full[:need]), ("closed form", n, levels, need)
             if n < 65536:
                 got16 = np.zeros(need, np.int32)
                 hc.hc_sort_prefix_u16(key.ctypes.data_as(C.c_void_p), n, need, got16.ctypes.data_as(C.c_void_p))
@@ -80,4 +83,6 @@ def test_sort_prefix_adversarial_patterns(hc):
         for need in (1, 120, 200, 2500, n):
             got = np.zeros(need, np.int32)
             hc.hc_sort_prefix(key.ctypes.data_as(C.c_void_p), n, need, got.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(got, full[:need])
+            hc.hc_sort_prefix_closed(key.ctypes.data_as(C.c_void_p), n, need, got.ctypes.data_as(C.c_void_p))
             assert np.array_equal(got, full[:need])
