@@ -34,7 +34,7 @@ struct SparseGeom<false> {  // minutiae: <= 120 candidates
 };
 template <>
 struct SparseGeom<true> {  // texture: <= 200 candidates
-    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 8192;
+    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 7168;
 };
 
 template <bool LOOKUP>
@@ -45,6 +45,8 @@ struct SparseWork {
     float lo[G::MAXP], ro[G::MAXP];
     float b[G::MAXP], c[G::MAXP];
     short2 lxy[G::MAXP], rxy[G::MAXP];
+    // texture graph only: the same coordinates as floats (exact), its pre-test runs on the fp32 pipes
+    float2 lxyf[LOOKUP ? G::MAXP : 1], rxyf[LOOKUP ? G::MAXP : 1];
     unsigned short li[G::MAXP], rj[G::MAXP];
     unsigned short row_start[G::MAXP], row_len[G::MAXP];
     unsigned short y[G::MAXP];    // candidates in std::sort order
@@ -58,32 +60,43 @@ struct SparseWork {
     unsigned short y2[32];
 };
 
-// Cheap, conservative pre-test of "H[a][b] may be non-zero" evaluated for ALL pairs; the exact entry is
-// then computed only for the survivors (~9 % of the pairs of a non-mated print), compacted so that the
-// expensive correctly-rounded square roots and divisions run on full warps.
+// Cheap, conservative pre-test of "H[a][b] may be non-zero" evaluated for ALL pairs; the exact entry is then
+// computed only for the survivors (~9 % of the pairs of a non-mated print), compacted so that the expensive
+// correctly-rounded square roots and divisions run on full warps.
+// Coordinates arrive as floats (small integers, exact) so that no integer->float conversion and no 64-bit
+// integer product is needed per pair.
 template <bool LOOKUP>
-__device__ __forceinline__ bool pair_may_connect(short2 la, short2 lb, short2 ra, short2 rb, const float* __restrict__ table) {
+__device__ __forceinline__ bool pair_may_connect(float2 la, float2 lb, float2 ra, float2 rb) {
+    const float dx1 = la.x - lb.x, dx2 = ra.x - rb.x, dy1 = la.y - lb.y, dy2 = ra.y - rb.y;  // exact
+    const float s1 = fmaf(dx1, dx1, dy1 * dy1), s2 = fmaf(dx2, dx2, dy2 * dy2);               // exact integers < 2^24
     if (LOOKUP) {
         // matcher.cpp:1246-1266 with table[dx][dy] = fl(16 sqrt(dx^2 + dy^2)): |d1 - d2| <= 30 needs
-        // (16 sqrt(s1) - 16 sqrt(s2))^2 <= 900, i.e. 64 (s1 + s2) - 225 <= 128 sqrt(s1 s2) with the integers
-        // s = dx^2 + dy^2 < 5000.  Tested in integers with the 225 widened to 232 (the table entries are
-        // rounded to fp32: relative 6e-8 on values <= 1110, far inside that margin); no table load.
-        const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
-        const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
-        if ((abs(dx1) >= kTableN) | (abs(dx2) >= kTableN) | (abs(dy1) >= kTableN) | (abs(dy2) >= kTableN)) return false;
-        const int s1 = dx1 * dx1 + dy1 * dy1, s2 = dx2 * dx2 + dy2 * dy2;
-        const int t = 64 * (s1 + s2) - 232;  // < 2^20
-        return t <= 0 || (long long)t * t <= 16384ll * s1 * s2;
+        // (sqrt(s1) - sqrt(s2))^2 <= (30/16)^2 = 3.515625, i.e. s1 + s2 - 3.515625 <= 2 sqrt(s1 s2), with s < 5000
+        // once every |dx|, |dy| is below 50 (:1257).  Tested with 3.625 (the table entries are rounded to fp32,
+        // relative 6e-8 on values <= 1110; t*t and 4*s1*s2 round with relative 6e-8 on values whose exact
+        // versions differ by > 1e-5 relative whenever the two constants matter): never rejects a connected pair.
+        if (fmaxf(fmaxf(fabsf(dx1), fabsf(dx2)), fmaxf(fabsf(dy1), fabsf(dy2))) >= (float)kTableN) return false;
+        const float t = (s1 + s2) - 3.625f;  // exact (multiples of 1/8 below 2^14)
+        return t <= 0.0f || t * t <= 4.0f * s1 * s2;
     } else {
         // |d1 - d2| <= 30.04  <=>  s1 + s2 - 30.04^2 <= 2 sqrt(s1 s2), with s = d^2 an exact integer below
-        // 2^24.  Rounding moves the comparison by < 0.2 squared pixels (coordinates are below 2^11), the
-        // margin over 30^2 is 2.4: nothing with |d1 - d2| <= 30 is rejected here.
-        const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
-        const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
-        const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);
+        // 2^23 (guarded below).  Rounding moves the comparison by < 0.2 squared pixels, the margin over 30^2 is
+        // 2.4: nothing with |d1 - d2| <= 30 is rejected here.
+        if (fmaxf(s1, s2) >= 8388608.0f) return true;  // images beyond 2048 px: leave the decision to the exact entry
         const float t = s1 + s2 - 902.4f;
         return t <= 0.0f || t * t <= 4.0f * s1 * s2;
     }
+}
+
+// The minutiae graph keeps its candidates' pixel coordinates as short2 in registers (4 chunks) and forms the
+// squared distances in integers; measured faster there than the float-coordinate form above (14.4 vs 13.9 ms).
+__device__ __forceinline__ bool pair_may_connect_px(short2 la, short2 lb, short2 ra, short2 rb) {
+    const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
+    const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
+    const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);  // exact below 2^24
+    if (fmaxf(s1, s2) >= 8388608.0f) return true;  // images beyond 2048 px: leave the decision to the exact entry
+    const float t = s1 + s2 - 902.4f;
+    return t <= 0.0f || t * t <= 4.0f * s1 * s2;
 }
 
 // H entry of the distance-consistency graph for candidates a, b (symmetric in a, b), exact.
@@ -143,12 +156,17 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
 
     // ---- CSR rows of the distance-consistency graph ----
     {
-        short2 clxy[CH], crxy[CH];
+        // column coordinates of the pre-test: registers for the minutiae graph (4 chunks), shared memory for the
+        // texture graph (7 chunks would cost 28 registers and an occupancy step)
+        constexpr int CHR = LOOKUP ? 1 : CH;
+        short2 clxy[CHR], crxy[CHR];
+        if (!LOOKUP) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int j = lane + 32 * c;
-            clxy[c] = (j < num) ? w.lxy[j] : make_short2(0, 0);
-            crxy[c] = (j < num) ? w.rxy[j] : make_short2(0, 0);
+            for (int c = 0; c < CHR; ++c) {
+                const int j = lane + 32 * c;
+                clxy[c] = (j < num) ? w.lxy[j] : make_short2(0, 0);
+                crxy[c] = (j < num) ? w.rxy[j] : make_short2(0, 0);
+            }
         }
         const int wbase = warp * CAPW;
         int used = 0;
@@ -159,13 +177,23 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             const short2 la = w.lxy[i], ra = w.rxy[i];
             // pass 1: columns that may connect to row i, ascending
             int cnt = 0;
+            if constexpr (LOOKUP) {
+                const float2 laf = w.lxyf[i], raf = w.rxyf[i];
+                for (int j = lane; j - lane < num; j += 32) {
+                    const bool pass = j < num && j != i && pair_may_connect<LOOKUP>(laf, w.lxyf[j], raf, w.rxyf[j]);
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
+                    cnt += __popc(m);
+                }
+            } else {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int j = lane + 32 * c;
-                const bool pass = j < num && j != i && pair_may_connect<LOOKUP>(la, clxy[c], ra, crxy[c], table);
-                const unsigned m = __ballot_sync(0xffffffffu, pass);
-                if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
-                cnt += __popc(m);
+                for (int c = 0; c < CH; ++c) {
+                    const int j = lane + 32 * c;
+                    const bool pass = j < num && j != i && pair_may_connect_px(la, clxy[c], ra, crxy[c]);
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
+                    cnt += __popc(m);
+                }
             }
             __syncwarp();
             // pass 2: exact entries of the survivors, compacted again (an exact entry can still be 0)
@@ -501,6 +529,8 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
         const int i = w.li[tid], j = w.rj[tid];
         w.lxy[tid] = P.lat_xy[(size_t)q * P.lt_stride + i];
         w.rxy[tid] = P.gal_xy[gbase + j];
+        w.lxyf[tid] = make_float2((float)w.lxy[tid].x, (float)w.lxy[tid].y);
+        w.rxyf[tid] = make_float2((float)w.rxy[tid].x, (float)w.rxy[tid].y);
         w.lo[tid] = P.lat_ori[(size_t)q * P.lt_stride + i];
         w.ro[tid] = P.gal_ori[gbase + j];
     }

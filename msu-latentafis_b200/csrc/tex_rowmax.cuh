@@ -48,7 +48,7 @@ namespace lafis {
 
 constexpr int kRowTile = 32;
 constexpr int kRowmaxThreads = 512;
-constexpr int kRowmaxRegs = 96;  // leaves 16K registers per SM for the selection / graph CTAs that run beside it
+constexpr int kRowmaxRegs = 128;  // the whole register file: at 96 ptxas serialised the 16 gathers of a batch and sank the code-word look-ahead
 constexpr int kLutBytes = 4 * 256 * 128;  // [s][code][b][row] u8
 constexpr int kWindow = 18;               // see the bound above: 16.002 + 0.4, rounded up with slack
 constexpr int kWindowQ = (kWindow + 3) / 4 + 1;  // the same window on distances tracked as Dq >> 2: floor((x + W) / 4) <= floor(x / 4) + ceil(W / 4) + 1
@@ -245,11 +245,25 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
         // ---- stream the slice: warps draw templates from a shared counter (template sizes vary 600..1000 points) ----
         const int t_begin = slice * slice_len;
         const int t_end = min(P.n_chunk, t_begin + slice_len);
+        // A warp always holds its next template too and asks L2 for that template's code words (12.8 KB) while it
+        // works on the current one: the stream loop's own look-ahead of one batch then never waits for DRAM.
+        auto draw = [&]() {
+            int t = 0;
+            if (lane == 0) t = t_begin + atomicAdd(&s_next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t < t_end) {
+                const uint32_t b = P.tex_off[P.g0 + t];
+                const int bytes = (int)(P.tex_off[P.g0 + t + 1] - b) * 16;
+                const char* p = reinterpret_cast<const char*>(P.codes + b);
+                for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            }
+            return t;
+        };
+        int tl_next = draw();
         for (;;) {
-            int tl = 0;
-            if (lane == 0) tl = t_begin + atomicAdd(&s_next, 1);
-            tl = __shfl_sync(0xffffffffu, tl, 0);
+            const int tl = tl_next;
             if (tl >= t_end) break;
+            tl_next = draw();
             const int g = P.g0 + tl;
             const uint32_t base = P.tex_off[g];
             const int n = (int)(P.tex_off[g + 1] - base);
@@ -264,11 +278,15 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) f1[u] = f2[u] = f3[u] = 0xffffffffu;
 
-            uint4 cnext = __ldg(cp);
+            // code words two batches ahead: wherever ptxas places the load inside the body, a full batch of work
+            // lies between it and its first use
+            uint4 cnext = __ldg(cp), cnext2 = cnext;
+            if (16 < n) cnext2 = __ldg(cp + 16);
             uint32_t bp = 0;  // batch index in both fields
             for (int j0 = 0; j0 < n; j0 += 16, bp += 0x00010001u) {
                 const uint4 c = cnext;
-                if (j0 + 16 < n) cnext = __ldg(cp + j0 + 16);
+                cnext = cnext2;
+                if (j0 + 32 < n) cnext2 = __ldg(cp + j0 + 32);
                 // The integer ALU pipe (PRMT, IADD3, VIMNMX: 16 lanes/clk per scheduler) would bound this loop, so the
                 // additions go to the FMA pipe (IMAD with a run-time multiplier of 1); the two pipes end up level.
                 uint32_t all[4] = {0u, 0u, 0u, 0u}, odd[4] = {0u, 0u, 0u, 0u};
