@@ -48,4 +48,60 @@ struct DeviceLatents {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Block-wide bitonic sort of np2 (a power of two, >= 32, <= NT * KPT) 64-bit keys in shared memory, descending.
+// Compare-exchange distances below 32 stay inside a warp: each thread keeps its key(s) in registers and
+// exchanges them by shuffle, so only the distances >= 32 go through shared memory and a block barrier
+// (6 barriers instead of 28 for 128 keys).  Every thread of the block must call; ends with a barrier.
+template <int NT, int KPT>
+__device__ __forceinline__ void block_bitonic_desc(unsigned long long* skey, int np2) {
+    const int tid = threadIdx.x;
+    unsigned long long mine[KPT];
+    auto load_keys = [&]() {
+#pragma unroll
+        for (int e = 0; e < KPT; ++e) {
+            const int i = tid + e * NT;
+            mine[e] = (i < np2) ? skey[i] : 0ull;
+        }
+    };
+    auto store_keys = [&]() {
+#pragma unroll
+        for (int e = 0; e < KPT; ++e) {
+            const int i = tid + e * NT;
+            if (i < np2) skey[i] = mine[e];
+        }
+    };
+    auto exchange = [&](int k, int j) {  // one compare-exchange step at distance j < 32 of merge size k
+#pragma unroll
+        for (int e = 0; e < KPT; ++e) {
+            const int i = tid + e * NT;
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine[e], j);
+            const bool take_max = ((i & j) == 0) == ((i & k) == 0);
+            mine[e] = ((mine[e] > other) == take_max) ? mine[e] : other;
+        }
+    };
+    load_keys();
+    for (int k = 2; k <= 32; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) exchange(k, j);
+    store_keys();
+    __syncthreads();
+    for (int k = 64; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            for (int t = tid; t < np2 / 2; t += NT) {
+                const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+                const bool desc = ((lo & k) == 0);
+                const unsigned long long a = skey[lo], b = skey[hi];
+                if ((a < b) == desc) {
+                    skey[lo] = b;
+                    skey[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+        load_keys();
+        for (int j = 16; j > 0; j >>= 1) exchange(k, j);
+        store_keys();
+        __syncthreads();
+    }
+}
+
 }  // namespace lafis

@@ -477,19 +477,7 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
             keys[i] = k;
         }
         __syncthreads();
-        for (int k = 2; k <= np2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < np2 / 2; t += NT) {
-                    const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
-                    const bool desc = ((lo & k) == 0);
-                    const unsigned long long a = keys[lo], b = keys[hi];
-                    if ((a < b) == desc) {
-                        keys[lo] = b;
-                        keys[hi] = a;
-                    }
-                }
-                __syncthreads();
-            }
+        block_bitonic_desc<NT, 1024 / NT>(keys, np2);
         // a tie that reaches into the first 200 positions makes the permutation introsort-specific
         if (tid < kTopCorrTex && (keys[tid] >> 32) == (keys[tid + 1] >> 32)) w.tie = 1;
         __syncthreads();

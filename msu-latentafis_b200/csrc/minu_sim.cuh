@@ -33,7 +33,8 @@ namespace lafis {
 constexpr int kSimThreads = 512;
 constexpr int kSelThreads = 256;
 constexpr int kSelMaxCand = 512;  // sorted in the histogram's 4 KB (512 x 8 B)
-constexpr int kSelBins = 1024;  // float bits >> 20 of values in (0, 1]
+constexpr int kSelBins = 1024;  // 64 bins per binade over [2^-16, 1): float bits >> 17, offset; smaller values share bin 0
+constexpr uint32_t kSelBinBase = (127u - 16u) << 6;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
@@ -368,7 +369,8 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
             if (s > 0.0f) {
                 const float a = approx_key(s, l, rsum[j]);
                 Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
-                atomicAdd(&hist[min(__float_as_uint(a) >> 20, (uint32_t)(kSelBins - 1))], 1);
+                const uint32_t hb = __float_as_uint(a) >> 17;
+                atomicAdd(&hist[hb > kSelBinBase ? min(hb - kSelBinBase, (uint32_t)(kSelBins - 1)) : 0u], 1);
             }
         }
     }
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
         if (lane == 0) {
             s_bin = bin;
             // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side)
-            s_thr = __uint_as_float((uint32_t)bin << 20) * (1.0f - 4e-6f);
+            // (bin 0 collects everything below 2^-16: its lower edge is 0)
+            s_thr = bin > 0 ? __uint_as_float(((uint32_t)bin + kSelBinBase) << 17) * (1.0f - 4e-6f) : 0.0f;
         }
     }
     __syncthreads();
@@ -448,19 +451,7 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
         skey[c] = k;
     }
     __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < np2 / 2; t += kSelThreads) {
-                const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
-                const bool desc = ((lo & k) == 0);
-                const unsigned long long a = skey[lo], b = skey[hi];
-                if ((a < b) == desc) {
-                    skey[lo] = b;
-                    skey[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
+    block_bitonic_desc<kSelThreads, kSelMaxCand / kSelThreads>(skey, np2);
     // equal values among the first K (or straddling position K) make the order introsort-specific
     if (tid < K && tid + 1 < nc && (skey[tid] >> 32) == (skey[tid + 1] >> 32)) s_flag = 1;
     __syncthreads();
