@@ -53,6 +53,7 @@ struct SparseWork {
     unsigned short sel[G::MAXP];  // accepted candidates, acceptance order
     unsigned char cols[G::CAP];
     unsigned char rowj[G::NT / 32][G::MAXP];  // per-warp scratch: columns that passed the cheap test
+    unsigned long long skeys[G::MAXP <= 128 ? 128 : 256];  // (b, index) keys of the candidate ranking
     float f;
     int overflow, tie, nsel;
     // orientation stage (<= 32 survivors), only touched when the introsort replay is needed
@@ -76,27 +77,27 @@ __device__ __forceinline__ bool pair_may_connect(float2 la, float2 lb, float2 ra
         // relative 6e-8 on values <= 1110; t*t and 4*s1*s2 round with relative 6e-8 on values whose exact
         // versions differ by > 1e-5 relative whenever the two constants matter): never rejects a connected pair.
         if (fmaxf(fmaxf(fabsf(dx1), fabsf(dx2)), fmaxf(fabsf(dy1), fabsf(dy2))) >= (float)kTableN) return false;
-        const float t = (s1 + s2) - 3.625f;  // exact (multiples of 1/8 below 2^14)
-        return t <= 0.0f || t * t <= 4.0f * s1 * s2;
+        const float u = fmaxf(fmaf(s1 + s2, 0.5f, -1.8125f), 0.0f);  // (s1 + s2 - 3.625) / 2, exact
+        return u * u <= s1 * s2;
     } else {
         // |d1 - d2| <= 30.04  <=>  s1 + s2 - 30.04^2 <= 2 sqrt(s1 s2), with s = d^2 an exact integer below
-        // 2^23 (guarded below).  Rounding moves the comparison by < 0.2 squared pixels, the margin over 30^2 is
-        // 2.4: nothing with |d1 - d2| <= 30 is rejected here.
-        if (fmaxf(s1, s2) >= 8388608.0f) return true;  // images beyond 2048 px: leave the decision to the exact entry
-        const float t = s1 + s2 - 902.4f;
-        return t <= 0.0f || t * t <= 4.0f * s1 * s2;
+        // 2^23 (coordinates below 2048: jobs with larger ones go to the dense kernel).  Rounding moves the
+        // comparison by < 0.2 squared pixels, the margin over 30^2 is 2.4: nothing with |d1 - d2| <= 30 is
+        // rejected here.
+        const float u = fmaxf(fmaf(s1 + s2, 0.5f, -451.2f), 0.0f);
+        return u * u <= s1 * s2;
     }
 }
 
 // The minutiae graph keeps its candidates' pixel coordinates as short2 in registers (4 chunks) and forms the
 // squared distances in integers; measured faster there than the float-coordinate form above (14.4 vs 13.9 ms).
+// |d1 - d2| <= 30.04  <=>  (s1 + s2 - 902.4) / 2 <= sqrt(s1 s2); coordinates are below 2048 (larger ones: dense kernel).
 __device__ __forceinline__ bool pair_may_connect_px(short2 la, short2 lb, short2 ra, short2 rb) {
     const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
     const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
-    const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);  // exact below 2^24
-    if (fmaxf(s1, s2) >= 8388608.0f) return true;  // images beyond 2048 px: leave the decision to the exact entry
-    const float t = s1 + s2 - 902.4f;
-    return t <= 0.0f || t * t <= 4.0f * s1 * s2;
+    const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);  // exact below 2^23
+    const float u = fmaxf(fmaf(s1 + s2, 0.5f, -451.2f), 0.0f);                              // (s1 + s2 - 902.4) / 2
+    return u * u <= s1 * s2;
 }
 
 // H entry of the distance-consistency graph for candidates a, b (symmetric in a, b), exact.
@@ -248,18 +249,27 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
         __syncthreads();
     }
 
-    // ---- order by b descending with std::sort's permutation ----
-    if (tid < num) {
-        const float mk = w.b[tid];
-        int rank = 0;
-        bool tie = false;
-        for (int k = 0; k < num; ++k) {
-            const float ok = w.b[k];
-            rank += (ok > mk) || (ok == mk && k < tid);
-            tie |= (ok == mk && k != tid);
+    // ---- order by b descending with std::sort's permutation: (value desc, index asc) keys through the block's
+    //      bitonic sort; equal values that the greedy pass can reach need the introsort replay ----
+    {
+        constexpr int P2 = G::MAXP <= 128 ? 128 : 256;
+        static_assert(P2 <= NT && G::MAXN <= P2, "one key per thread");
+        unsigned long long k = 0ull;  // padding keys sort last
+        if (tid < num) {
+            uint32_t u = __float_as_uint(w.b[tid]);  // b >= 0: the bit pattern orders like the value
+            if (u == 0x80000000u) u = 0u;
+            k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffu - (unsigned)tid);
         }
-        w.y[rank] = (unsigned short)tid;
-        if (tie && num > 16 && !((double)mk < 0.0001)) w.tie = 1;
+        if (tid < P2) w.skeys[tid] = k;
+        __syncthreads();
+        block_bitonic_desc<NT, 1>(w.skeys, P2);
+        if (tid < num) {
+            const unsigned long long me = w.skeys[tid];
+            w.y[tid] = (unsigned short)(0xffffu - (unsigned)(me & 0xffffu));
+            if (tid + 1 < num && num > 16 && (me >> 32) == (w.skeys[tid + 1] >> 32) &&
+                !((double)__uint_as_float((uint32_t)(me >> 32)) < 0.0001))
+                w.tie = 1;
+        }
     }
     __syncthreads();
     if (w.tie) {
@@ -406,6 +416,7 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         w.overflow = 0;
         w.tie = 0;
     }
+    int big = 0;
     if (tid < num) {
         const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
         const int i = (int)(ij >> 16), j = (int)(ij & 0xffffu);
@@ -417,8 +428,15 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         w.rxy[tid] = P.gal_xy[go];
         w.lo[tid] = P.lat_ori[lo];
         w.ro[tid] = P.gal_ori[go];
+        // the pre-test squares coordinate differences in fp32: exact only below 2048 px
+        // (coordinates in [0, 2048): differences below 2048, squared distances below 2^23)
+        big = ((unsigned)(int)w.lxy[tid].x | (unsigned)(int)w.lxy[tid].y | (unsigned)(int)w.rxy[tid].x |
+               (unsigned)(int)w.rxy[tid].y) >= 2048u;
     }
-    __syncthreads();
+    if (__syncthreads_or(big)) {  // larger images: the dense kernel evaluates every entry exactly
+        if (tid == 0) ov.jobs[atomicAdd(ov.count, 1)] = (int)oidx;
+        return;
+    }
     float score;
     const bool ok = sparse_cascade<false>(w, num, nullptr, &score);
     if (tid == 0) {
