@@ -150,6 +150,18 @@ LAFIS_API int lafis_match(lafis_ctx* ctx, lafis_latents* latents, int topk, lafi
  * returned device pointers stay valid until the next match on this context. */
 LAFIS_API int lafis_match_device(lafis_ctx* ctx, lafis_latents* latents, int topk, const void** d_hits,
                                  const float** d_all_scores);
+/* ---- surviving minutiae correspondences of ONE (latent, gallery template) pair.
+ *      Replaces the save_corr branch of One2One_minutiae_matching (matcher.cpp:497-505), which
+ *      One2List_matching runs for the 24 best gallery templates (:322-327): for each of the three selected
+ *      minutiae templates (:380) the list corr3 of LSS_R_Fast2 (:495), in the order it is written to
+ *      "<corr_file>_<i>.csv".  xy_out[(slot * LAFIS_MAX_CORR + k) * 4 + {0,1,2,3}] = latent x, latent y,
+ *      rolled x, rolled y of correspondence k; counts_out[slot] = number of correspondences (their
+ *      similarities sum to component score[slot]).  Host memory; gallery_index is local to this context.
+ *      Returns the latent's status when it is not LAFIS_OK (no output then). ---- */
+#define LAFIS_MAX_CORR 120
+LAFIS_API int lafis_correspondences(lafis_ctx* ctx, lafis_latents* latents, int q, int gallery_index,
+                                    int16_t* xy_out /* [3][LAFIS_MAX_CORR][4] */, int* counts_out /* [3] */);
+
 /* merge per-shard rank lists (n_lists lists of topk entries per latent, concatenated per latent)
  * into global ones with the (score desc, index asc) rule; host memory. */
 LAFIS_API int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n_lists, int topk, lafis_hit* out);
@@ -164,6 +176,10 @@ LAFIS_API int lafis_merge_hits_device(lafis_ctx* ctx, const void* d_gathered, in
  *      lafis_one2list_matching  replaces PQ::Matcher::One2List_matching,  matcher.cpp:216-337:
  *        writes <score_path><latent stem>.csv = "filename,score" + up to 24 rows
  *        <rank>"<rolled path>",<score>; returns 0, -1 (no *.dat in rolled_dir), 1 (latent empty).
+ *        For those (up to) 24 templates it also writes the correspondence files of :322-327,
+ *        "<corr_prefix>corr<latent stem>_<rolled stem>_<i>.csv" (i = 0, 1, 2; rows "lx,ly,rx,ry"), where
+ *        corr_prefix is the environment variable LAFIS_CORR_PATH if set, else score_path (the reference
+ *        hard-codes "/LatentAFIS/scores/").
  *      lafis_list2list_matching replaces PQ::Matcher::List2List_matching, matcher.cpp:96-214:
  *        one CSV per latent with one row "<rolled path>",<score %.3f> per gallery file in
  *        directory order, -1.000 for entries the reference leaves unscored.

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <filesystem>
 #include <fstream>
 #include <iomanip>
@@ -96,8 +97,10 @@ LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_templat
     }
     std::vector<float> scores((size_t)G, -1.0f);
     rc = lafis_match(ctx, L, 0, nullptr, scores.data(), nullptr);
-    lafis_latents_free(L);
-    if (rc != LAFIS_OK) return rc;
+    if (rc != LAFIS_OK) {
+        lafis_latents_free(L);
+        return rc;
+    }
     for (int j = 0; j < G; ++j)
         if (scores[j] == -1.0f && lafis_gallery_status(ctx, j) != LAFIS_TPL_OK &&
             lafis_gallery_status(ctx, j) != LAFIS_TPL_TRUNCATED)
@@ -112,11 +115,34 @@ LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_templat
     std::cout << "Match Results" << std::endl;
     std::cout << "----------------" << std::endl;
     std::cout << "Rank     Filename      Score" << std::endl;
+    // correspondence files of the 24 best (matcher.cpp:322-327, written by :497-505); the reference's prefix
+    // "/LatentAFIS/scores/" is configurable here
+    const char* corr_env = std::getenv("LAFIS_CORR_PATH");
+    const std::string corr_prefix = corr_env ? std::string(corr_env) : std::string(score_path);
+    std::vector<int16_t> corr_xy((size_t)3 * LAFIS_MAX_CORR * 4);
     for (int j = 0; j < 24 && j < G; ++j) {
         const fs::path rolled(lafis_gallery_path(ctx, ind[j]));
         output << std::to_string(j + 1) << rolled << "," << scores[ind[j]] << std::endl;
+        const int gst = lafis_gallery_status(ctx, ind[j]);
+        if (gst == LAFIS_TPL_OK || gst == LAFIS_TPL_TRUNCATED) {  // the reference returns before matching an empty print (:388-391)
+            int counts[3] = {0, 0, 0};
+            rc = lafis_correspondences(ctx, L, 0, ind[j], corr_xy.data(), counts);
+            if (rc != LAFIS_OK) {
+                lafis_latents_free(L);
+                return rc;
+            }
+            const std::string corr_file = corr_prefix + "corr" + latent_file.stem().string() + "_" + rolled.stem().string();
+            for (int i = 0; i < 3; ++i) {
+                std::ofstream co(corr_file + "_" + std::to_string(i) + ".csv");
+                for (int k = 0; k < counts[i]; ++k) {
+                    const int16_t* e = &corr_xy[((size_t)i * LAFIS_MAX_CORR + k) * 4];
+                    co << e[0] << "," << e[1] << "," << e[2] << "," << e[3] << std::endl;
+                }
+            }
+        }
         std::cout << std::to_string(j + 1) << "        " << rolled.filename() << "       " << scores[ind[j]] << std::endl;
     }
+    lafis_latents_free(L);
     output.close();
     const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
     std::cout << "Total matching duration (ms): " << span.count() << std::endl;

@@ -123,10 +123,13 @@ __device__ __forceinline__ void greedy_select(GraphWork<MAXN>& w, const float* k
 // The whole pruning cascade for one candidate list held in w (v, li, rj, coordinates, orientations).
 // LOOKUP selects the texture flavour (table distances, 3 iterations) or the minutiae flavour
 // (Euclidean distances, 5 iterations).  Returns the component score (valid in thread 0).
+// *n_final (thread 0) = number of surviving correspondences; they are w.sel[0..n) into the *2 arrays, in the
+// order the reference pushes them into corr3 (and writes them to its correspondence file, matcher.cpp:497-505).
 template <int MAXN, int NT, bool LOOKUP>
-__device__ float prune_cascade(GraphWork<MAXN>& w, int num, float* H, const float* table) {
+__device__ float prune_cascade(GraphWork<MAXN>& w, int num, float* H, const float* table, int* n_final = nullptr) {
     const int tid = threadIdx.x;
     constexpr int LD = MAXN;
+    if (n_final) *n_final = 0;
     if (num <= 0) return 0.0f;
 
     // ---- distance-consistency graph ----
@@ -244,6 +247,7 @@ __device__ float prune_cascade(GraphWork<MAXN>& w, int num, float* H, const floa
     float score = 0.0f;
     if (tid == 0)
         for (int s = 0; s < w.nsel; ++s) score = f_add(score, w.v2[w.sel[s]]);
+    if (n_final) *n_final = w.nsel;
     return score;
 }
 
@@ -265,6 +269,10 @@ struct GraphMinuParams {
     int g0, n_chunk;
     int G;        // templates resident on this device
     float* comp;  // [Q][G][4] = score[0], score[1], score[2], score[28]
+    // optional (dense kernel only): the surviving correspondences of every job, [job][kTopCorrMinu] x
+    // {latent x, latent y, rolled x, rolled y} and their count - the reference's save_corr output
+    short4* corr_out = nullptr;
+    int* corr_out_n = nullptr;
 };
 
 constexpr int kGraphMinuThreads = 128;
@@ -301,8 +309,17 @@ __global__ void __launch_bounds__(kGraphMinuThreads) graph_minu_dense_kernel(Gra
             w.ro[tid] = P.gal_ori[go];
         }
         __syncthreads();
-        const float score = prune_cascade<kTopCorrMinu, kGraphMinuThreads, false>(w, num, H, nullptr);
+        int n_final = 0;
+        const float score = prune_cascade<kTopCorrMinu, kGraphMinuThreads, false>(w, num, H, nullptr, &n_final);
         if (tid == 0) P.comp[((size_t)q * P.G + P.g0 + tl) * 4 + slot] = score;
+        if (P.corr_out) {  // n_final is uniform across the block
+            if (tid == 0) P.corr_out_n[oidx] = n_final;
+            if (tid < n_final) {
+                const int s = w.sel[tid];
+                P.corr_out[oidx * kTopCorrMinu + tid] =
+                    make_short4((short)w.lx2[s], (short)w.ly2[s], (short)w.rx2[s], (short)w.ry2[s]);
+            }
+        }
     }
 }
 

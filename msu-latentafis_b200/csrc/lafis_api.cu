@@ -125,6 +125,8 @@ struct lafis_ctx {
     int* d_ov_count = nullptr;    // [2]
     DevBuf<float> comp;
     DevBuf<float> final_scores;
+    DevBuf<short4> corr_xy;       // lafis_correspondences: surviving correspondences of the 3 minutiae components
+    DevBuf<int> corr_xy_n;
     DevBuf<unsigned long long> keys_a, keys_b;
     DevBuf<HitDev> hits;
     DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
@@ -1089,6 +1091,115 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     return LAFIS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// correspondences of one (latent, gallery template) pair - the reference's save_corr output
+// (matcher.cpp:322-327 for the 24 best of a 1-vs-N search, written by :497-505)
+// ---------------------------------------------------------------------------------------------------
+static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, short4* h_xy, int* h_n) {
+    const int Q = L->n, G = c->gal.n;
+    if (G <= 0) return fail(c, LAFIS_ERR_NO_GALLERY, "no gallery resident");
+    if (q < 0 || q >= Q || gi < 0 || gi >= G) return fail(c, LAFIS_ERR_ARG, "latent %d / gallery template %d out of range", q, gi);
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    unsigned char* A = nullptr;
+    if (L->resident && L->owner == c) {
+        A = L->d_arena;
+    } else {
+        LAFIS_CUDA(c, c->lat_arena.reserve(L->arena_bytes));
+        A = c->lat_arena.p;
+        LAFIS_CUDA(c, cudaMemcpyAsync(A, L->pinned, L->arena_bytes, cudaMemcpyHostToDevice, st));
+    }
+    const int maxL = std::max(1, L->max_slot_n), maxLp = (maxL + 3) & ~3;
+    const int maxNp = std::max(4, (c->max_nR + 3) & ~3);
+    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 160;
+    int b_double = 1;
+    if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
+    const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
+    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp);
+    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem;
+    const size_t slow_smem = minu_select_slow_smem_bytes(maxL, maxNp, slow_dense);
+    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || sel_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
+        return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE, "minutiae templates of %d x %d points exceed the shared-memory tiles", L->max_slot_n, c->max_nR);
+    const size_t job_stride = (size_t)maxL * maxNp;
+    const unsigned jobs = (unsigned)Q * 3u;
+    LAFIS_CUDA(c, c->corr_v.reserve((size_t)jobs * kTopCorrMinu));
+    LAFIS_CUDA(c, c->corr_ij.reserve((size_t)jobs * kTopCorrMinu));
+    LAFIS_CUDA(c, c->corr_n.reserve(jobs));
+    LAFIS_CUDA(c, c->sim.reserve((size_t)jobs * job_stride));
+    LAFIS_CUDA(c, c->slow_jobs.reserve(jobs));
+    LAFIS_CUDA(c, c->ov_minu.reserve(jobs));
+    LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
+    LAFIS_CUDA(c, c->corr_xy.reserve((size_t)jobs * kTopCorrMinu));
+    LAFIS_CUDA(c, c->corr_xy_n.reserve(jobs));
+
+    MinuSimParams P;
+    P.slot_n = reinterpret_cast<int*>(A + L->o_slot_n);
+    P.slot_off = reinterpret_cast<uint32_t*>(A + L->o_slot_off);
+    P.lat_desT = reinterpret_cast<float*>(A + L->o_minu_desT);
+    P.lat_status = reinterpret_cast<int*>(A + L->o_status);
+    P.Q = Q;
+    P.minu_off = c->gal.minu_off;
+    P.minu_n = c->gal.minu_n;
+    P.minu_desT = c->gal.minu_desT;
+    P.g0 = gi;
+    P.n_chunk = 1;
+    P.a_slot_stride = a_slot_stride;
+    P.b_buf_stride = b_buf_stride;
+    P.b_double = b_double;
+    P.S = c->sim.p;
+    P.job_stride = job_stride;
+    minu_sim_kernel<<<1, kSimThreads, sim_smem, st>>>(P);
+    MinuSelectParams R;
+    R.slot_n = P.slot_n;
+    R.lat_status = P.lat_status;
+    R.Q = Q;
+    R.minu_n = c->gal.minu_n;
+    R.g0 = gi;
+    R.n_chunk = 1;
+    R.S = c->sim.p;
+    R.job_stride = job_stride;
+    R.max_nL = maxL;
+    R.max_np = maxNp;
+    R.slow_dense = slow_dense ? 1 : 0;
+    R.corr_v = c->corr_v.p;
+    R.corr_ij = c->corr_ij.p;
+    R.corr_n = c->corr_n.p;
+    R.slow_count = c->d_slow_count;
+    R.slow_jobs = c->slow_jobs.p;
+    LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
+    minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
+    minu_select_slow_kernel<<<std::min<unsigned>(jobs, (unsigned)c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
+    // every job of latent q goes through the dense graph kernel, which can list its survivors
+    const int h_jobs[3] = {q * 3 + 0, q * 3 + 1, q * 3 + 2};
+    const int h_count = 3;
+    LAFIS_CUDA(c, cudaMemcpyAsync(c->ov_minu.p, h_jobs, sizeof h_jobs, cudaMemcpyHostToDevice, st));
+    LAFIS_CUDA(c, cudaMemcpyAsync(c->d_ov_count, &h_count, sizeof(int), cudaMemcpyHostToDevice, st));
+    GraphMinuParams Gp;
+    Gp.corr_v = c->corr_v.p;
+    Gp.corr_ij = c->corr_ij.p;
+    Gp.corr_n = c->corr_n.p;
+    Gp.slot_off = P.slot_off;
+    Gp.lat_xy = reinterpret_cast<short2*>(A + L->o_minu_xy);
+    Gp.lat_ori = reinterpret_cast<float*>(A + L->o_minu_ori);
+    Gp.minu_off = c->gal.minu_off;
+    Gp.gal_xy = c->gal.minu_xy;
+    Gp.gal_ori = c->gal.minu_ori;
+    Gp.g0 = gi;
+    Gp.n_chunk = 1;
+    Gp.G = G;
+    Gp.comp = c->comp.p;
+    Gp.corr_out = c->corr_xy.p;
+    Gp.corr_out_n = c->corr_xy_n.p;
+    graph_minu_dense_kernel<<<3, kGraphMinuThreads, kGraphMinuSmem, st>>>(Gp, c->d_ov_count, c->ov_minu.p);
+    c->stats.kernel_launches += 4;
+    LAFIS_CUDA(c, cudaGetLastError());
+    LAFIS_CUDA(c, cudaMemcpyAsync(h_n, c->corr_xy_n.p + q * 3, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LAFIS_CUDA(c, cudaMemcpyAsync(h_xy, c->corr_xy.p + (size_t)q * 3 * kTopCorrMinu, 3 * kTopCorrMinu * sizeof(short4),
+                                  cudaMemcpyDeviceToHost, st));
+    LAFIS_CUDA(c, cudaStreamSynchronize(st));
+    return LAFIS_OK;
+}
+
 // after the stream has been synchronised: device times of the last match
 static void collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
@@ -1142,6 +1253,14 @@ int lafis_match(lafis_ctx* c, lafis_latents* L, int topk, lafis_hit* hits, float
     LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
     collect_times(c);
     return LAFIS_OK;
+}
+
+int lafis_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gallery_index, int16_t* xy_out, int* counts_out) {
+    if (!c || !L || !xy_out || !counts_out) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    static_assert(sizeof(short4) == 4 * sizeof(int16_t), "short4 layout");
+    for (int s = 0; s < 3; ++s) counts_out[s] = 0;
+    if (q >= 0 && q < L->n && L->status[q] != LAFIS_OK) return L->status[q];
+    return run_correspondences(c, L, q, gallery_index, reinterpret_cast<short4*>(xy_out), counts_out);
 }
 
 int lafis_merge_hits_device(lafis_ctx* c, const void* d_gathered, int n_latents, int n_lists, int topk, void* d_out) {

@@ -72,7 +72,8 @@ EXPORTS = [
     "lafis_gallery_load_dir", "lafis_gallery_load_files", "lafis_gallery_set_packed", "lafis_gallery_size",
     "lafis_gallery_path", "lafis_gallery_status", "lafis_gallery_bytes", "lafis_gallery_get_template",
     "lafis_latents_load_files", "lafis_latents_from_packed", "lafis_latents_count", "lafis_latents_status",
-    "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device", "lafis_merge_hits", "lafis_merge_hits_device",
+    "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device",
+    "lafis_correspondences", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
     "lafis_get_stats", "lafis_set_streams", "lafis_stream",
 ]
@@ -116,6 +117,7 @@ def load_library():
     L.lafis_latents_make_resident.argtypes = [vp, vp]
     L.lafis_match.argtypes = [vp, vp, ci, vp, vp, vp]
     L.lafis_match_device.argtypes = [vp, vp, ci, C.POINTER(vp), C.POINTER(vp)]
+    L.lafis_correspondences.argtypes = [vp, vp, ci, ci, vp, vp]
     L.lafis_merge_hits.argtypes = [vp, ci, ci, ci, vp]
     L.lafis_merge_hits_device.argtypes = [vp, vp, ci, ci, ci, vp]
     L.lafis_one2list_matching.argtypes = [vp, cp, cp, cp]
@@ -382,6 +384,15 @@ class Matcher:
             comps = np.zeros((Q, G, 4), np.float32)
         self._chk(self.L.lafis_match(self.ctx, latents.h, topk, _ptr(hits), _ptr(scores), _ptr(comps)))
         return {"hits": hits, "scores": scores, "components": comps}
+
+    def correspondences(self, latents: Latents, q: int, gallery_index: int):
+        """Surviving minutiae correspondences of latent q against one gallery template, the reference's
+        save_corr output (matcher.cpp:497-505): -> 3 arrays (one per selected minutiae template) of shape
+        (n_i, 4) = latent x, latent y, rolled x, rolled y."""
+        xy = np.zeros((3, 120, 4), np.int16)
+        n = np.zeros(3, np.int32)
+        self._chk(self.L.lafis_correspondences(self.ctx, latents.h, q, gallery_index, _ptr(xy), _ptr(n)))
+        return [xy[s, :n[s]].copy() for s in range(3)]
 
     def match_device(self, latents: Latents, topk: int = 0):
         """Scores and rank lists stay in HBM: returns (d_hits, d_scores) raw device pointers."""

@@ -119,6 +119,15 @@ int ref_score_gallery(void* m, void* latent, void** rolled, int n, float* finals
     return bad ? -100 : 0;
 }
 
+// The save_corr branch (matcher.cpp:497-505) as One2List_matching drives it for its 24 best (:322-327): writes
+// "<corr_file>_<i>.csv", i = 0..2, one "lx,ly,rx,ry" row per surviving correspondence.
+int ref_save_corr(void* m, void* latent, void* rolled, const char* corr_file) {
+    LatentFPTemplate* l = static_cast<LatentFPTemplate*>(latent);
+    RolledFPTemplate* r = static_cast<RolledFPTemplate*>(rolled);
+    std::vector<float> score;
+    return static_cast<Matcher*>(m)->One2One_matching_selected_templates(*l, *r, score, true, std::string(corr_file));
+}
+
 int ref_one2list(void* m, const char* latent_file, const char* gallery_dir, const char* score_dir) {
     return static_cast<Matcher*>(m)->One2List_matching(latent_file, gallery_dir, score_dir);
 }

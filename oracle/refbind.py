@@ -85,6 +85,28 @@ class RefMatcher:
         rc = self.L.ref_score_gallery(self.m, latent, arr, n, fin.ctypes.data, comps.ctypes.data, nthreads)
         return rc, fin, comps
 
+    def correspondences(self, latent, rolled):
+        """corr3 of the three selected minutiae templates as the reference writes them (matcher.cpp:497-505):
+        -> (rc, [3 arrays of shape (n_i, 4): latent x, latent y, rolled x, rolled y])"""
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="lafis_corr_")
+        try:
+            prefix = os.path.join(tmp, "corr")
+            self.L.ref_save_corr.restype = C.c_int
+            self.L.ref_save_corr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+            rc = self.L.ref_save_corr(self.m, latent, rolled, prefix.encode())
+            out = []
+            for i in range(3):
+                p = f"{prefix}_{i}.csv"
+                rows = []
+                if os.path.isfile(p):
+                    rows = [[int(x) for x in line.split(",")] for line in open(p).read().split() if line]
+                out.append(np.array(rows, np.int16).reshape(-1, 4))
+            return rc, out
+        finally:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+
     def prune(self, which, latent, latent_tpl, rolled, v, li, rj):
         v = np.ascontiguousarray(v, np.float32)
         li = np.ascontiguousarray(li, np.int32)

@@ -6,7 +6,8 @@ Run in the build container (needs /root/reference and oracle/_ref built by oracl
 
 Inputs: synthetic templates in the reference's .dat layout (SURVEY.md §8d generators, written by
 msu-latentafis_b200/templates.py) and the shipped PQ codebook.  Outputs recorded: for every
-(latent, rolled) pair the return code, the four component scores and the fused score of
+(latent, rolled) pair the return code, the four component scores, the surviving minutiae correspondences
+(save_corr, matcher.cpp:497-505) and the fused score of
 PQ::Matcher::One2One_matching_selected_templates (matching/matcher.cpp:376-417, fusion :188), obtained
 through oracle/_ref/libref_matcher.so; and the score files the reference CLI oracle/_ref/match writes
 in both modes.  The .npz stores the template files as raw bytes so that every consumer goes through
@@ -91,11 +92,20 @@ def main():
     pair_rc = np.zeros((len(lnames), len(gnames)), np.int32)
     pair_comp = np.zeros((len(lnames), len(gnames), 4), np.float32)
     pair_final = np.zeros((len(lnames), len(gnames)), np.float32)
+    # surviving correspondences (the save_corr output, matcher.cpp:497-505) of every scored pair
+    corr_n = np.zeros((len(lnames), len(gnames), 3), np.int32)
+    corr_rows = []
     for i, l in enumerate(lnames):
         lh, _ = R.load_latent(os.path.join(ldir, l + ".dat"))
         for j, rh in enumerate(rhandles):
             rc, comp, fin = R.score_pair(lh, rh)
             pair_rc[i, j], pair_comp[i, j], pair_final[i, j] = rc, comp, fin
+            if rc == 0 and rolled_rc[j] == 0:
+                _, lists = R.correspondences(lh, rh)
+                for s in range(3):
+                    corr_n[i, j, s] = len(lists[s])
+                    corr_rows.append(lists[s])
+    corr_xy = np.concatenate(corr_rows).astype(np.int16) if corr_rows else np.zeros((0, 4), np.int16)
     R.close()
 
     # ---- score files from the reference CLI (it insists on ../afis.config relative to the cwd) ----
@@ -125,6 +135,9 @@ def main():
         "pair_rc": pair_rc, "pair_comp": pair_comp, "pair_final": pair_final,
         "n2n_files": np.array(sorted(n2n)), "n2n_text": np.array([n2n[k] for k in sorted(n2n)]),
         "one2n_text": np.array(one2n),
+        # corr_xy: rows "latent x, latent y, rolled x, rolled y" of all pairs with corr_n > 0, concatenated in
+        # (latent, gallery, slot) order; corr_n[latent, gallery, slot] = rows of that list
+        "corr_n": corr_n, "corr_xy": corr_xy,
     }
     for g in gnames:
         out["gal_" + g] = blob(os.path.join(gdir, g + ".dat"))

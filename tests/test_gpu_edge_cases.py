@@ -116,3 +116,25 @@ def test_cli_binary_matches_reference_score_files(pkg, built, golden, tmp_path):
     assert r.returncode == 0 and "Match Results" in r.stdout
     first = open(os.path.join(sdir, "lB.csv")).read().split("\n")[1]
     assert first.startswith('1"') and "r01_mateB.dat" in first
+
+
+def test_large_images_take_the_dense_graph_kernel(pkg, built, golden, oracle):
+    """Minutiae coordinates beyond 2048 px (and negative ones): the sparse graph kernel's fp32 pre-test is only exact
+    below 2048, such jobs must be routed to the dense kernel and still match the oracle bit for bit."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(5200 + k) for k in range(6)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(95, raws[1]), T.synth_latent(96, raws[4], n_minu=50, n_tex_pts=90)]
+
+    def stretch(t, f, shift):
+        for m in t.minu:
+            m.x = (m.x.astype(np.int32) * f + shift).astype(np.int16)
+            m.y = (m.y.astype(np.int32) * f + shift).astype(np.int16)
+        return t
+
+    rolled = [stretch(r, 3, 0) if k != 2 else stretch(r, 1, -500) for k, r in enumerate(rolled)]  # one with negative x, y
+    latents = [stretch(l, 3, 0) for l in latents]
+    assert max(int(r.minu[0].x.max()) for r in rolled) > 2048
+    st = _run(pkg, cb, latents, rolled, oracle)
+    assert st["kernel_launches"] > 0

@@ -42,6 +42,65 @@ def test_golden_pairs_bit_exact(pkg, matcher, golden, tmp_path):
         assert np.array_equal(out["hits"][i]["score"], got_final[i][out["hits"][i]["index"]])
 
 
+def test_correspondences_match_the_reference_save_corr(pkg, matcher, golden, tmp_path):
+    """lafis_correspondences against the lists the reference writes with save_corr (matcher.cpp:497-505), for every
+    scored pair of the golden set, and the files the 1-vs-N driver writes for its 24 best (:322-327)."""
+    gdir, ldir = write_golden_files(golden, str(tmp_path))
+    gnames = [str(g) for g in golden["gallery_names"]]
+    lnames = [str(l) for l in golden["latent_names"]]
+    matcher.load_gallery_files([os.path.join(gdir, g + ".dat") for g in gnames])
+    L = matcher.load_latents([os.path.join(ldir, l + ".dat") for l in lnames])
+    corr_n, corr_xy = golden["corr_n"], golden["corr_xy"]
+    comp = matcher.match(L, want_components=True)["components"]
+    at = 0
+    checked = 0
+    for i, l in enumerate(lnames):
+        for j, g in enumerate(gnames):
+            scored = golden["pair_rc"][i, j] == 0 and golden["rolled_load_rc"][j] == 0
+            want = []
+            if scored:
+                for s in range(3):
+                    want.append(corr_xy[at:at + corr_n[i, j, s]])
+                    at += corr_n[i, j, s]
+            if not scored or g in UB_GALLERY:
+                continue
+            got = matcher.correspondences(L, i, j)
+            for s in range(3):
+                assert np.array_equal(got[s], want[s]), (l, g, s, got[s], want[s])
+                assert (len(got[s]) > 0) == (comp[i, j, s] > 0)
+            checked += 1
+    assert at == len(corr_xy) and checked > 40
+    # the driver's files for the 24 best of latent lA
+    sdir = os.path.join(str(tmp_path), "scores1") + os.sep
+    os.makedirs(sdir)
+    assert matcher.One2List_matching(os.path.join(ldir, "lA.dat"), gdir, sdir) == 0
+    rows = open(os.path.join(sdir, "lA.csv")).read().split()[1:]
+    i = lnames.index("lA")
+    first = {}
+    a = 0
+    for ii in range(len(lnames)):
+        for j in range(len(gnames)):
+            if golden["pair_rc"][ii, j] == 0 and golden["rolled_load_rc"][j] == 0:
+                if ii == i:
+                    first[j] = a
+                a += int(corr_n[ii, j].sum())
+    n_files = 0
+    for row in rows:
+        stem = os.path.basename(row.split('"')[1])[:-4]
+        j = gnames.index(stem)
+        if j not in first or stem in UB_GALLERY:
+            continue
+        a = first[j]
+        for s in range(3):
+            path = os.path.join(sdir, f"corrlA_{stem}_{s}.csv")
+            text = open(path).read()
+            want = "".join(",".join(str(int(v)) for v in r) + "\n" for r in corr_xy[a:a + corr_n[i, j, s]])
+            assert text == want, (stem, s)
+            a += corr_n[i, j, s]
+            n_files += 1
+    assert n_files >= 30
+
+
 def test_synthetic_vs_oracle_bit_exact(pkg, matcher, golden, oracle):
     T = pkg.templates
     cb = golden["codebook"]
