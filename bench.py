@@ -343,10 +343,12 @@ def run_b200_arm(args):
                         "row_gathers_per_s": gathers / (float(stage_ms[0]) / 1e3) if stage_ms[0] > 0 else 0,
                         "fp32_gather_roofline_per_s": smem_peak,
                         "frac_of_fp32_gather_roofline": (gathers / (float(stage_ms[0]) / 1e3) / smem_peak) if stage_ms[0] > 0 else 0,
-                        "smem_bandwidth_frac": (gathers * 2 / (float(stage_ms[0]) / 1e3) / (smem_peak * 4)) if stage_ms[0] > 0 else 0,
+                        "smem_bandwidth_frac": (gathers * 1 / (float(stage_ms[0]) / 1e3) / (smem_peak * 4)) if stage_ms[0] > 0 else 0,
                         "note": "nLt*nRt*16 (row, column, sub-quantizer) look-ups per pair; the fp32 formulation of "
                                 "SURVEY.md 8d is bounded by 148 SM x 32 banks x sm_max_mhz 4-byte gathers/s; this kernel "
-                                "gathers 2-byte quantised entries (smem_bandwidth_frac = bytes moved / 128 B/clk/SM)"},
+                                "gathers 1-byte quantised entries, 16 rows per LDS.128 (smem_bandwidth_frac = bytes moved / "
+                                "128 B/clk/SM); it is bound by instruction issue (ncu: 78 % issue-active), not by the "
+                                "shared-memory pipe"},
         "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:8])},
         "kernel_ms_note": "per-kernel CUDA-event durations from two extra steps with all kernels serialised on one stream "
                           "(lafis_set_streams(1)); the timed region overlaps the texture chain with the minutiae chain on "

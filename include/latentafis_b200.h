@@ -210,7 +210,7 @@ typedef struct {
     /* cumulative exactness bookkeeping since the context was created */
     uint64_t minu_replays;    /* top-120 selections that needed the introsort replay (ties) */
     uint64_t tex_replays;     /* top-200 row selections that needed the introsort replay */
-    uint64_t tex_queued;      /* texture row-max: (row, column) candidates queued by the integer filter */
+    uint64_t tex_queued;      /* texture row-max: (row, column) candidates the 8-bit integer filter let through */
     uint64_t tex_exact;       /* ... of which re-evaluated exactly in fp32 */
     uint64_t tex_overflow;    /* ... (warp, template) visits whose queue overflowed: evaluated exactly in full */
     uint64_t tex_templates;   /* ... (warp, template) visits in total */
