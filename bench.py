@@ -207,7 +207,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO would put extra lines on stdout before the JSON line
+        os.environ["NCCL_DEBUG"] = "NONE"  # VERSION/WARN/INFO put "NCCL version ..." and more on stdout before the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = entry.load_package()
