@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/latentafis_b200.h"
@@ -486,28 +487,77 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
     if (n == 0) return fail(c, LAFIS_ERR_NO_TEMPLATES, "no rolled templates");
     const long long lo = (long long)n * shard_rank / shard_count, hi = (long long)n * (shard_rank + 1) / shard_count;
     const int m = (int)(hi - lo);
-    std::vector<uint32_t> minu_off(m + 1, 0), tex_off(m + 1, 0);
-    std::vector<int16_t> mx, my, tx, ty;
-    std::vector<float> mori, mdes, tori;
-    std::vector<uint8_t> codes;
+    // Parse with all host cores: every thread reads a contiguous range of files into its own packed part
+    // (the reference re-parses every rolled file for every latent, matcher.cpp:173/:278; here it happens once),
+    // then the parts are copied to their place in the final arrays, again in parallel.
+    struct Part {
+        std::vector<uint32_t> n_minu, n_tex;  // per template
+        std::vector<int16_t> mx, my, tx, ty;
+        std::vector<float> mori, mdes, tori;
+        std::vector<uint8_t> codes;
+    };
+    const int n_threads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 64, m / 32 + 1}));
+    std::vector<Part> parts(n_threads);
     std::vector<int8_t> status(m);
     std::vector<std::string> kept(m);
-    for (int t = 0; t < m; ++t) {
-        RolledTemplate R;
-        read_rolled_dat(paths[lo + t], R);
-        kept[t] = paths[lo + t];
-        status[t] = (int8_t)R.status;
-        mx.insert(mx.end(), R.minu.x.begin(), R.minu.x.end());
-        my.insert(my.end(), R.minu.y.begin(), R.minu.y.end());
-        mori.insert(mori.end(), R.minu.ori.begin(), R.minu.ori.end());
-        mdes.insert(mdes.end(), R.minu.des.begin(), R.minu.des.end());
-        tx.insert(tx.end(), R.tex.x.begin(), R.tex.x.end());
-        ty.insert(ty.end(), R.tex.y.begin(), R.tex.y.end());
-        tori.insert(tori.end(), R.tex.ori.begin(), R.tex.ori.end());
-        codes.insert(codes.end(), R.tex.codes.begin(), R.tex.codes.end());
-        minu_off[t + 1] = (uint32_t)mx.size();
-        tex_off[t + 1] = (uint32_t)tx.size();
+    auto range_lo = [&](int i) { return (int)((long long)m * i / n_threads); };
+    auto parse = [&](int i) {
+        Part& P = parts[i];
+        for (int t = range_lo(i); t < range_lo(i + 1); ++t) {
+            RolledTemplate R;
+            read_rolled_dat(paths[lo + t], R);
+            kept[t] = paths[lo + t];
+            status[t] = (int8_t)R.status;
+            P.mx.insert(P.mx.end(), R.minu.x.begin(), R.minu.x.end());
+            P.my.insert(P.my.end(), R.minu.y.begin(), R.minu.y.end());
+            P.mori.insert(P.mori.end(), R.minu.ori.begin(), R.minu.ori.end());
+            P.mdes.insert(P.mdes.end(), R.minu.des.begin(), R.minu.des.end());
+            P.tx.insert(P.tx.end(), R.tex.x.begin(), R.tex.x.end());
+            P.ty.insert(P.ty.end(), R.tex.y.begin(), R.tex.y.end());
+            P.tori.insert(P.tori.end(), R.tex.ori.begin(), R.tex.ori.end());
+            P.codes.insert(P.codes.end(), R.tex.codes.begin(), R.tex.codes.end());
+            P.n_minu.push_back((uint32_t)R.minu.x.size());
+            P.n_tex.push_back((uint32_t)R.tex.x.size());
+        }
+    };
+    auto run_parallel = [&](auto&& fn) {
+        std::vector<std::thread> pool;
+        for (int i = 1; i < n_threads; ++i) pool.emplace_back(fn, i);
+        fn(0);
+        for (std::thread& th : pool) th.join();
+    };
+    run_parallel(parse);
+    std::vector<uint32_t> minu_off(m + 1, 0), tex_off(m + 1, 0);
+    std::vector<size_t> part_m(n_threads + 1, 0), part_t(n_threads + 1, 0);
+    for (int i = 0; i < n_threads; ++i) {
+        part_m[i + 1] = part_m[i] + parts[i].mx.size();
+        part_t[i + 1] = part_t[i] + parts[i].tx.size();
+        int t = range_lo(i);
+        for (size_t k = 0; k < parts[i].n_minu.size(); ++k, ++t) {
+            minu_off[t + 1] = minu_off[t] + parts[i].n_minu[k];
+            tex_off[t + 1] = tex_off[t] + parts[i].n_tex[k];
+        }
     }
+    const size_t tot_m = part_m[n_threads], tot_t = part_t[n_threads];
+    if (tot_m > 0xffffffffull / 2 || tot_t > 0xffffffffull / 2) return fail(c, LAFIS_ERR_ARG, "gallery shard too large for 32-bit offsets");
+    std::vector<int16_t> mx(tot_m), my(tot_m), tx(tot_t), ty(tot_t);
+    std::vector<float> mori(tot_m), mdes(tot_m * kDesLen), tori(tot_t);
+    std::vector<uint8_t> codes(tot_t * 16);
+    run_parallel([&](int i) {
+        const Part& P = parts[i];
+        auto cp = [](void* d, const void* s_, size_t b) {
+            if (b) std::memcpy(d, s_, b);
+        };
+        cp(mx.data() + part_m[i], P.mx.data(), 2 * P.mx.size());
+        cp(my.data() + part_m[i], P.my.data(), 2 * P.my.size());
+        cp(mori.data() + part_m[i], P.mori.data(), 4 * P.mori.size());
+        cp(mdes.data() + part_m[i] * kDesLen, P.mdes.data(), 4 * P.mdes.size());
+        cp(tx.data() + part_t[i], P.tx.data(), 2 * P.tx.size());
+        cp(ty.data() + part_t[i], P.ty.data(), 2 * P.ty.size());
+        cp(tori.data() + part_t[i], P.tori.data(), 4 * P.tori.size());
+        cp(codes.data() + part_t[i] * 16, P.codes.data(), P.codes.size());
+        parts[i] = Part();  // release the part as soon as it has been copied
+    });
     lafis_packed_gallery g{};
     g.n_templates = m;
     g.minu_off = minu_off.data();

@@ -211,3 +211,38 @@ def test_drivers_write_reference_score_files(pkg, matcher, golden, tmp_path):
     assert open(os.path.join(sdir1, "lE_empty.csv")).read().strip() == "0"
     assert matcher.One2List_matching(os.path.join(ldir, "lA.dat"), str(tmp_path / "nowhere_dir_empty"), sdir1) == -1 \
         if os.makedirs(str(tmp_path / "nowhere_dir_empty"), exist_ok=True) is None else True
+
+
+def test_parallel_ingest_equals_packed_input(pkg, matcher, golden, tmp_path):
+    """lafis_gallery_load_files parses with several host threads (each a contiguous range of files): the resident
+    gallery must equal the one built from the same templates packed in memory, template by template and score by
+    score, including unreadable files in the middle of a range."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    n = 300
+    raws = [T.synth_rolled_raw(7000 + g, n_minu=20 + (g * 7) % 50, n_tex=30 + (g * 13) % 90) for g in range(n)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    paths = []
+    for g, r in enumerate(rolled):
+        p = os.path.join(str(tmp_path), f"g{g:04d}.dat")
+        if g in (17, 150, 299):
+            with open(p, "wb") as f:  # <= 10 bytes: the loader returns 1 (matcher.cpp:899-902)
+                f.write(b"\x01\x00")
+        else:
+            T.write_template(p, r)
+        paths.append(p)
+    latents = [T.synth_latent(70, raws[5], n_minu=15, n_tex_pts=25), T.synth_latent(71, raws[200], n_minu=18, n_tex_pts=33)]
+    L = matcher.latents_from_packed(pkg.pack_latents(latents))
+    matcher.load_gallery_files(paths)
+    assert matcher.gallery_size == n
+    from_files = matcher.match(L, topk=5)
+    for g in (0, 16, 18, 149, 151, 298):
+        a, b = matcher.gallery_template(g), rolled[g]
+        assert np.array_equal(a.minu[0].x, b.minu[0].x) and np.array_equal(a.minu[0].des, b.minu[0].des)
+        assert np.array_equal(a.tex[0].des, b.tex[0].des) and np.array_equal(a.tex[0].ori, b.tex[0].ori)
+    keep = [g for g in range(n) if g not in (17, 150, 299)]
+    matcher.set_gallery(pkg.pack_rolled([rolled[g] for g in keep]))
+    packed = matcher.match(L, topk=5)
+    assert np.array_equal(from_files["scores"][:, keep], packed["scores"])
+    assert (from_files["scores"][:, [17, 150, 299]] == -1.0).all()
+    assert from_files["hits"][0]["index"][0] == 5 and from_files["hits"][1]["index"][0] == 200
