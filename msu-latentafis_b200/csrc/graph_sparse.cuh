@@ -34,7 +34,7 @@ struct SparseGeom<false> {  // minutiae: <= 120 candidates
 };
 template <>
 struct SparseGeom<true> {  // texture: <= 200 candidates
-    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 7168;
+    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 5632;
 };
 
 template <bool LOOKUP>
