@@ -31,7 +31,7 @@
 namespace lafis {
 
 constexpr int kSimThreads = 512;
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 384;  // 12 warps per job, 4 jobs per SM (shared memory): 48 of 64 warp slots
 constexpr int kSelMaxCand = 512;  // sorted in the histogram's 4 KB (512 x 8 B)
 constexpr int kSelBins = 1024;  // 64 bins per binade over [2^-16, 1): float bits >> 17, offset; smaller values share bin 0
 constexpr uint32_t kSelBinBase = (127u - 16u) << 6;
@@ -279,7 +279,7 @@ __device__ __forceinline__ float approx_key(float s, float l, float r) {
     return s * rc;
 }
 
-__global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectParams P) {
+__global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kSelThreads / 32;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kSelThreads) minu_select_kernel(MinuSelectPara
         skey[c] = k;
     }
     __syncthreads();
-    block_bitonic_desc<kSelThreads, kSelMaxCand / kSelThreads>(skey, np2);
+    block_bitonic_desc<kSelThreads, (kSelMaxCand + kSelThreads - 1) / kSelThreads>(skey, np2);
     // equal values among the first K (or straddling position K) make the order introsort-specific
     if (tid < K && tid + 1 < nc && (skey[tid] >> 32) == (skey[tid + 1] >> 32)) s_flag = 1;
     __syncthreads();
