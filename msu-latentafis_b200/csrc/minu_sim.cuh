@@ -12,8 +12,8 @@
 // chosen per template (96..160 columns): per k four loads feed 8*NC multiply-adds.  S goes to HBM ([nL][np] per job) - ~115 KB per pair written once
 // and read once, far below what the path's fp32 issue rate lets HBM see.
 //
-// minu_select_kernel (K6 + K7).  One 256-thread CTA per (latent, template, slot), ~57 KB of shared
-// memory so that three CTAs share an SM and hide each other's barriers.  Column sums (i ascending) and
+// minu_select_kernel (K6 + K7).  One 384-thread CTA per (latent, template, slot), ~57 KB of shared
+// memory so that four CTAs share an SM and hide each other's barriers.  Column sums (i ascending) and
 // row sums (j ascending) by one thread per column / row over an odd-stride copy of S.  The 120 largest
 // normalised values S/(l_i + r_j - S + 1e-6) are found in two passes over an fp32 estimate of that
 // value (relative error < 1e-6): a 1024-bin histogram of the float bit patterns locates the bin of the
