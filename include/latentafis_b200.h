@@ -197,6 +197,23 @@ LAFIS_API void lafis_forget_gallery_dir(lafis_ctx* ctx);
  *      pointers when on_device != 0. ---- */
 LAFIS_API int lafis_pq_encode(lafis_ctx* ctx, const float* des, int64_t n, uint8_t* codes, int on_device);
 
+/* ---- enrollment of one rolled print: the tail of the reference's extraction pipeline,
+ *      TrainedPQEncoder.encode_multi (descriptor_PQ.py:19-27) on the texture descriptors followed by
+ *      Template2Bin_Byte_PQ_rolled (:178-272).  Coordinates arrive as the reference holds them, rows of
+ *      {x, y, orientation} in pixels; minutiae x, y are truncated to u16, texture points are written in block
+ *      units (u16)((x - 24) / 16) (:249-256).  The PQ codes are computed on the GPU with the context's codebook.
+ *      The file is readable by the reference matcher and by lafis_gallery_load_*. ---- */
+typedef struct {
+    int h, w, blkH, blkW;     /* image size and ridge-flow block grid (block sizes are clamped to 50) */
+    int n_minu;               /* <= 2000 are written */
+    const float* minu_xyo;    /* [n_minu][3] */
+    const float* minu_des;    /* [n_minu][96] */
+    int n_tex;
+    const float* tex_xyo;     /* [n_tex][3], pixels */
+    const float* tex_des;     /* [n_tex][96], PQ-encoded on the device */
+} lafis_rolled_features;
+LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* features, const char* out_path);
+
 /* ---- instrumentation ---- */
 typedef struct {
     uint64_t kernel_launches; /* kernels launched by this library since the context was created */

@@ -1,5 +1,6 @@
 #include "dat_format.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -202,6 +203,51 @@ int read_latent_dat(const std::string& path, LatentTemplate& out) {
         out.tex.des.resize((size_t)kMaxTexture * kDesLen);
     }
     return 0;
+}
+
+int write_rolled_dat(const std::string& path, int h, int w, int blkH, int blkW, const PointSet& minu, const PointSet& tex) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return -3;
+    bool ok = true;
+    auto put = [&](const void* p, size_t bytes) {
+        if (bytes) ok = ok && std::fwrite(p, 1, bytes, f) == bytes;
+    };
+    auto put_u16 = [&](unsigned v) {
+        const uint16_t x = (uint16_t)v;
+        put(&x, 2);
+    };
+    auto put_u8 = [&](unsigned v) {
+        const uint8_t x = (uint8_t)v;
+        put(&x, 1);
+    };
+    uint16_t header[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // descriptor_PQ.py:186-189
+    put(header, sizeof header);
+    put_u16((unsigned)h);
+    put_u16((unsigned)w);
+    put_u16((unsigned)std::min(blkH, 50));
+    put_u16((unsigned)std::min(blkW, 50));
+    put_u8(1);  // one minutiae template
+    const int nm = std::min(minu.n(), kMaxMinutiae);
+    put_u16((unsigned)nm);
+    if (nm > 0) {
+        put(minu.x.data(), 2 * (size_t)nm);
+        put(minu.y.data(), 2 * (size_t)nm);
+        put(minu.ori.data(), 4 * (size_t)nm);
+        put_u16(kDesLen);
+        put(minu.des.data(), 4 * (size_t)nm * kDesLen);
+    }
+    put_u8(1);  // one texture template
+    const int nt = std::min(tex.n(), kMaxMinutiae);
+    put_u16((unsigned)nt);
+    if (nt > 0) {
+        put(tex.x.data(), 2 * (size_t)nt);
+        put(tex.y.data(), 2 * (size_t)nt);
+        put(tex.ori.data(), 4 * (size_t)nt);
+        put_u16(kSubs);
+        put(tex.codes.data(), (size_t)nt * kSubs);
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? 0 : -3;
 }
 
 int read_codebook(const std::string& path, std::vector<float>& cw, int& subs, int& clusters, int& sub_dim) {

@@ -45,6 +45,12 @@ struct LatentTemplate {
 int read_rolled_dat(const std::string& path, RolledTemplate& out);
 int read_latent_dat(const std::string& path, LatentTemplate& out);
 
+// Writes a rolled template in the layout of Template2Bin_Byte_PQ_rolled (extraction/descriptor_PQ.py:178-272):
+// version-1 header, h, w, block sizes clamped to 50, one minutiae template (x, y as u16, ori f32, des f32[n][96]) and
+// one texture template (block coordinates u16, ori f32, 16 PQ codes per point).  At most 2000 points per template
+// are written (:213-214, :245-246).  Returns 0, or -3 on I/O error.
+int write_rolled_dat(const std::string& path, int h, int w, int blkH, int blkW, const PointSet& minu, const PointSet& tex);
+
 // u16 subs, u16 clusters, u16 sub_dim, f32[subs][clusters][sub_dim]; returns 0 or a negative LAFIS_ERR_*
 int read_codebook(const std::string& path, std::vector<float>& codewords, int& subs, int& clusters, int& sub_dim);
 

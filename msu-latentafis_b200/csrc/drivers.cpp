@@ -149,6 +149,37 @@ LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_templat
     return LAFIS_OK;
 }
 
+LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* F, const char* out_path) {
+    if (!ctx || !F || !out_path || F->n_minu < 0 || F->n_tex < 0 || (F->n_minu > 0 && (!F->minu_xyo || !F->minu_des)) ||
+        (F->n_tex > 0 && (!F->tex_xyo || !F->tex_des)))
+        return LAFIS_ERR_ARG;
+    PointSet minu, tex;
+    const int nm = std::min(F->n_minu, kMaxMinutiae), nt = std::min(F->n_tex, kMaxMinutiae);
+    minu.x.resize(nm);
+    minu.y.resize(nm);
+    minu.ori.resize(nm);
+    for (int i = 0; i < nm; ++i) {  // np.uint16(x): truncation (descriptor_PQ.py:221-229)
+        minu.x[i] = (int16_t)(uint16_t)F->minu_xyo[3 * i];
+        minu.y[i] = (int16_t)(uint16_t)F->minu_xyo[3 * i + 1];
+        minu.ori[i] = F->minu_xyo[3 * i + 2];
+    }
+    minu.des.assign(F->minu_des, F->minu_des + (size_t)nm * kDesLen);
+    tex.x.resize(nt);
+    tex.y.resize(nt);
+    tex.ori.resize(nt);
+    for (int i = 0; i < nt; ++i) {  // block units (descriptor_PQ.py:249-256)
+        tex.x[i] = (int16_t)(uint16_t)((F->tex_xyo[3 * i] - 24.0f) / 16.0f);
+        tex.y[i] = (int16_t)(uint16_t)((F->tex_xyo[3 * i + 1] - 24.0f) / 16.0f);
+        tex.ori[i] = F->tex_xyo[3 * i + 2];
+    }
+    tex.codes.resize((size_t)nt * kSubs);
+    if (nt > 0) {
+        const int rc = lafis_pq_encode(ctx, F->tex_des, nt, tex.codes.data(), 0);
+        if (rc != LAFIS_OK) return rc;
+    }
+    return write_rolled_dat(out_path, F->h, F->w, F->blkH, F->blkW, minu, tex) == 0 ? LAFIS_OK : LAFIS_ERR_IO;
+}
+
 LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
                                        const char* score_path) {
     if (!ctx || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;

@@ -58,6 +58,12 @@ class _PackedLatents(C.Structure):
                 ("tex_ori", C.c_void_p), ("tex_des", C.c_void_p)]
 
 
+class _RolledFeatures(C.Structure):
+    _fields_ = [("h", C.c_int), ("w", C.c_int), ("blkH", C.c_int), ("blkW", C.c_int), ("n_minu", C.c_int),
+                ("minu_xyo", C.c_void_p), ("minu_des", C.c_void_p), ("n_tex", C.c_int), ("tex_xyo", C.c_void_p),
+                ("tex_des", C.c_void_p)]
+
+
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_scored", C.c_uint64), ("last_match_ms", C.c_float),
                 ("last_stage_ms", C.c_float * 8), ("minu_replays", C.c_uint64), ("tex_replays", C.c_uint64),
@@ -75,6 +81,7 @@ EXPORTS = [
     "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device",
     "lafis_correspondences", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
+    "lafis_enroll_rolled",
     "lafis_get_stats", "lafis_set_streams", "lafis_stream",
 ]
 
@@ -125,6 +132,7 @@ def load_library():
     L.lafis_forget_gallery_dir.argtypes = [vp]
     L.lafis_forget_gallery_dir.restype = None
     L.lafis_pq_encode.argtypes = [vp, vp, C.c_int64, vp, ci]
+    L.lafis_enroll_rolled.argtypes = [vp, C.POINTER(_RolledFeatures), cp]
     L.lafis_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.lafis_set_streams.argtypes = [vp, ci]
     L.lafis_stream.argtypes = [vp]
@@ -423,6 +431,14 @@ class Matcher:
             return codes
         self._chk(self.L.lafis_pq_encode(self.ctx, int(des), int(n), int(codes_ptr), 1))
         return None
+
+    def enroll_rolled(self, out_path: str, minu_xyo, minu_des, tex_xyo, tex_des, h: int = 800, w: int = 768,
+                      blkH: int = 50, blkW: int = 48) -> None:
+        """Tail of the reference's enrollment (descriptor_PQ.py:19-27 + :178-272): PQ-encodes the texture
+        descriptors on the GPU and writes the rolled template file.  *_xyo: [n, 3] rows of x, y (pixels), orientation."""
+        a = [np.ascontiguousarray(v, np.float32) for v in (minu_xyo, minu_des, tex_xyo, tex_des)]
+        F = _RolledFeatures(h, w, blkH, blkW, len(a[0]), _ptr(a[0]), _ptr(a[1]), len(a[2]), _ptr(a[2]), _ptr(a[3]))
+        self._chk(self.L.lafis_enroll_rolled(self.ctx, C.byref(F), out_path.encode()))
 
     def stats(self) -> dict:
         s = _Stats()

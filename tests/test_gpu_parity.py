@@ -246,3 +246,47 @@ def test_parallel_ingest_equals_packed_input(pkg, matcher, golden, tmp_path):
     assert np.array_equal(from_files["scores"][:, keep], packed["scores"])
     assert (from_files["scores"][:, [17, 150, 299]] == -1.0).all()
     assert from_files["hits"][0]["index"][0] == 5 and from_files["hits"][1]["index"][0] == 200
+
+
+def test_enroll_rolled_writes_the_reference_layout(pkg, matcher, golden, tmp_path):
+    """lafis_enroll_rolled (GPU PQ encoder + Template2Bin_Byte_PQ_rolled layout, descriptor_PQ.py:19-27, :178-272):
+    byte-identical to the Python writer fed with numpy nearest-centroid codes, accepted by the reference's loader
+    when oracle/_ref is present, and scored like the same template packed in memory."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(8100 + g, n_minu=40 + 9 * g, n_tex=150 + 60 * g) for g in range(4)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    paths = []
+    for g, (raw, want) in enumerate(zip(raws, rolled)):
+        m0 = raw.minu
+        minu_xyo = np.stack([m0.x.astype(np.float32) + 0.25, m0.y.astype(np.float32) + 0.75, m0.ori], axis=1)  # truncated
+        tex_xyo = np.stack([raw.tex_x.astype(np.float32) * 16 + 24 + 3, raw.tex_y.astype(np.float32) * 16 + 24, raw.tex_ori], axis=1)
+        p = os.path.join(str(tmp_path), f"enrolled{g}.dat")
+        matcher.enroll_rolled(p, minu_xyo, m0.des, tex_xyo, raw.tex_des, h=want.h, w=want.w, blkH=want.blkH, blkW=want.blkW)
+        q = os.path.join(str(tmp_path), f"python{g}.dat")
+        T.write_template(q, want)
+        assert open(p, "rb").read() == open(q, "rb").read(), g
+        paths.append(p)
+    latents = [T.synth_latent(90, raws[2], n_minu=30, n_tex_pts=60)]
+    L = matcher.latents_from_packed(pkg.pack_latents(latents))
+    matcher.load_gallery_files(paths)
+    a = matcher.match(L, topk=2)
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    b = matcher.match(L, topk=2)
+    assert np.array_equal(a["scores"], b["scores"]) and a["hits"][0]["index"][0] == 2
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refbind
+    if refbind.available():
+        cbp = os.path.join(str(tmp_path), "cb.dat")
+        T.write_codebook(cbp, cb)
+        R = refbind.RefMatcher(cbp)
+        lp = os.path.join(str(tmp_path), "lat.dat")
+        T.write_template(lp, latents[0])
+        lh, _ = R.load_latent(lp)
+        for g, p in enumerate(paths):
+            rh, rc = R.load_rolled(p)
+            assert rc == 0
+            _, _, fin = R.score_pair(lh, rh)
+            assert fin == a["scores"][0, g]
+        R.close()
