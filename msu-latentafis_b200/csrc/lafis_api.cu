@@ -965,7 +965,16 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.b_double = b_double;
             P.S = c->sim.p;
             P.job_stride = job_stride;
-            minu_sim_kernel<<<std::min(n_chunk, c->sm_count), kSimThreads, sim_smem, st>>>(P);
+            {
+                int g = c->sm_count, r = Q;  // gcd(Q, SMs)
+                while (r) {
+                    const int t = g % r;
+                    g = r;
+                    r = t;
+                }
+                P.parts = std::max(1, std::min(c->sm_count / g, n_chunk));
+            }
+            minu_sim_kernel<<<std::min(Q * P.parts, c->sm_count), kSimThreads, sim_smem, st>>>(P);
             end(1, st);
             begin(2, st);
             MinuSelectParams R;
@@ -1198,7 +1207,8 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     P.b_double = b_double;
     P.S = c->sim.p;
     P.job_stride = job_stride;
-    minu_sim_kernel<<<1, kSimThreads, sim_smem, st>>>(P);
+    P.parts = 1;
+    minu_sim_kernel<<<std::min(Q, c->sm_count), kSimThreads, sim_smem, st>>>(P);
     MinuSelectParams R;
     R.slot_n = P.slot_n;
     R.lat_status = P.lat_status;
