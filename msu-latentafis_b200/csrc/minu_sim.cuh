@@ -303,31 +303,30 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
     __shared__ int s_order[kTopCorrMinu];
 
     const float* Sg = P.S + job * P.job_stride;
-    {   // S is [nL][np] with np % 4 == 0: a warp copies a row with 16-byte loads, two rows in flight
-        const int row4 = np >> 2;
+    {   // a warp copies two rows at a time with coalesced 4-byte loads: consecutive lanes then also store to
+        // consecutive banks of the odd-stride copy (16-byte loads needed four 4-way conflicting stores each)
         for (int i = warp; i < nL; i += 2 * NW) {
-            const float4* r0 = reinterpret_cast<const float4*>(Sg + (size_t)i * np);
-            const float4* r1 = reinterpret_cast<const float4*>(Sg + (size_t)(i + NW) * np);
+            const float* r0 = Sg + (size_t)i * np;
+            const float* r1 = Sg + (size_t)(i + NW) * np;
             const bool has1 = i + NW < nL;
-            float4 v0a = make_float4(0.f, 0.f, 0.f, 0.f), v0b = v0a, v1a = v0a, v1b = v0a;
-            if (lane < row4) v0a = __ldcs(r0 + lane);
-            if (lane + 32 < row4) v0b = __ldcs(r0 + lane + 32);
-            if (has1 && lane < row4) v1a = __ldcs(r1 + lane);
-            if (has1 && lane + 32 < row4) v1b = __ldcs(r1 + lane + 32);
-            auto put = [&](int row, int c4, float4 v) {
-                float* d = Ssm + row * ld + 4 * c4;
-                d[0] = v.x;
-                d[1] = v.y;
-                d[2] = v.z;
-                d[3] = v.w;
-            };
-            if (lane < row4) put(i, lane, v0a);
-            if (lane + 32 < row4) put(i, lane + 32, v0b);
-            if (has1 && lane < row4) put(i + NW, lane, v1a);
-            if (has1 && lane + 32 < row4) put(i + NW, lane + 32, v1b);
-            for (int c4 = lane + 64; c4 < row4; c4 += 32) {  // templates beyond 256 minutiae
-                put(i, c4, __ldcs(r0 + c4));
-                if (has1) put(i + NW, c4, __ldcs(r1 + c4));
+            float v0[5], v1[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int j = lane + 32 * k;
+                v0[k] = j < np ? __ldcs(r0 + j) : 0.0f;
+                v1[k] = (has1 && j < np) ? __ldcs(r1 + j) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int j = lane + 32 * k;
+                if (j < np) {
+                    Ssm[i * ld + j] = v0[k];
+                    if (has1) Ssm[(i + NW) * ld + j] = v1[k];
+                }
+            }
+            for (int j = lane + 160; j < np; j += 32) {  // templates beyond 160 minutiae
+                Ssm[i * ld + j] = __ldcs(r0 + j);
+                if (has1) Ssm[(i + NW) * ld + j] = __ldcs(r1 + j);
             }
         }
     }
