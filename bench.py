@@ -332,6 +332,7 @@ def run_b200_arm(args):
     achieved = kernel_bytes[dom] * Q * G / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     tex_points_mean = kernel_bytes["nRt_mean"]
     gathers = Q * G * nLt * tex_points_mean * 16
+    lat_minu = float(np.mean([sum(l.minu[i].n for i in (26, 2, 11) if i < len(l.minu)) for l in latents]))
     smem_peak = 148 * 32 * sm_max * 1e6
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -349,6 +350,22 @@ def run_b200_arm(args):
                                 "gathers 1-byte quantised entries, 16 rows per LDS.128 (smem_bandwidth_frac = bytes moved / "
                                 "128 B/clk/SM); it is bound by instruction issue (ncu: 78 % issue-active), not by the "
                                 "shared-memory pipe"},
+        # the resources that actually bind the two largest kernels (DESIGN.md "Which roofline binds"), from algorithmic
+        # operation counts and the same CUDA-event durations: fp32 instruction issue for the dot products (the
+        # reference's unfused multiply + add = 2 instructions per MAC on 128 fp32 lanes per SM), the shared-memory
+        # data pipe (128 B/clk/SM) for the 1-byte LUT gathers
+        "binding": [
+            {"kernel": "minu_sim_kernel", "resource": "fp32 instruction issue (2 instr/MAC, 148 SM x 128 lanes x sm_max_mhz)",
+             "achieved": (2.0 * lat_minu * 96 * kernel_bytes["nRm_mean"] * Q * G / (float(stage_ms[1]) / 1e3) / 1e12) if stage_ms[1] > 0 else 0,
+             "peak": 148 * 128 * sm_max * 1e6 / 1e12, "unit": "T lane-instr/s",
+             "frac": (2.0 * lat_minu * 96 * kernel_bytes["nRm_mean"] * Q * G / (float(stage_ms[1]) / 1e3) / (148 * 128 * sm_max * 1e6)) if stage_ms[1] > 0 else 0,
+             "note": "latent minutiae of the three selected templates x nRm gallery minutiae x 96-d, padding columns not counted"},
+            {"kernel": "tex_rowmax_kernel", "resource": "shared-memory data pipe (148 SM x 128 B/clk x sm_max_mhz)",
+             "achieved": (gathers / (float(stage_ms[0]) / 1e3) / 1e12) if stage_ms[0] > 0 else 0,
+             "peak": smem_peak * 4 / 1e12, "unit": "TB/s",
+             "frac": (gathers / (float(stage_ms[0]) / 1e3) / (smem_peak * 4)) if stage_ms[0] > 0 else 0,
+             "note": "nLt x nRt x 16 one-byte look-ups; the exact re-evaluations' uncoalesced loads use the same L1 data "
+                     "pipe (ncu: 77 % busy in total)"}],
         "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:8])},
         "kernel_ms_note": "per-kernel CUDA-event durations from two extra steps with all kernels serialised on one stream "
                           "(lafis_set_streams(1)); the timed region overlaps the texture chain with the minutiae chain on "
