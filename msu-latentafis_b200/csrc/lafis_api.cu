@@ -226,6 +226,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
         ok = ok && cudaMemset(c->d_slow, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
         TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
         TRY(cudaFuncSetAttribute(minu_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        TRY(cudaFuncSetAttribute(minu_sim_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(minu_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(minu_select_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(graph_minu_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGraphMinuSmem));
@@ -974,7 +975,10 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
                 }
                 P.parts = std::max(1, std::min(c->sm_count / g, n_chunk));
             }
-            minu_sim_kernel<<<std::min(Q * P.parts, c->sm_count), kSimThreads, sim_smem, st>>>(P);
+            if (Q > 1 && n_chunk < 16 * c->sm_count)  // few templates per CTA and chunk: balanced (latent, part) jobs
+                minu_sim_jobs_kernel<<<std::min(Q * P.parts, c->sm_count), kSimThreads, sim_smem, st>>>(P);
+            else
+                minu_sim_kernel<<<std::min(n_chunk, c->sm_count), kSimThreads, sim_smem, st>>>(P);
             end(1, st);
             begin(2, st);
             MinuSelectParams R;
@@ -1208,7 +1212,7 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     P.S = c->sim.p;
     P.job_stride = job_stride;
     P.parts = 1;
-    minu_sim_kernel<<<std::min(Q, c->sm_count), kSimThreads, sim_smem, st>>>(P);
+    minu_sim_kernel<<<1, kSimThreads, sim_smem, st>>>(P);
     MinuSelectParams R;
     R.slot_n = P.slot_n;
     R.lat_status = P.lat_status;

@@ -7,9 +7,11 @@
 // templates of a latent (matcher.cpp:380) against one gallery template per step.  Every output
 // accumulates k = 0..95 in order with an unfused fp32 multiply and add (the Eigen stand-in's order,
 // oracle/shim/Eigen/Dense).  The gallery's k-major descriptor blocks stream through a double buffer
-// with cp.async while the previous block is being multiplied; the latent's blocks stay resident for a whole job
-// (latent x part of the chunk).  Warp tile 16 x 16*NC, thread tile 8 x NC with NC = 6..10
-// chosen per template (96..160 columns): per k four loads feed 8*NC multiply-adds.  S goes to HBM ([nL][np] per job) - ~115 KB per pair written once
+// with cp.async while the previous block is being multiplied; the latent's blocks stay resident
+// (single latent) or are re-staged per latent (batches; minu_sim_jobs_kernel stages them once per
+// job instead).  Warp tile 16 x 16*NC, thread tile 8 x NC with NC = 6..10 chosen per template
+// (96..160 columns): per k four loads feed 8*NC multiply-adds.  S goes to HBM ([nL][np] per job) -
+// ~115 KB per pair written once
 // and read once, far below what the path's fp32 issue rate lets HBM see.
 //
 // minu_select_kernel (K6 + K7).  One 384-thread CTA per (latent, template, slot), ~57 KB of shared
@@ -142,6 +144,109 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, 
 }
 
 __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* A = reinterpret_cast<float*>(smem);        // [3][a_slot_stride]
+    float* B = A + 3 * (size_t)P.a_slot_stride;       // [1|2][b_buf_stride]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSimThreads / 32;
+    const int li = lane >> 4, lj = lane & 15;
+
+    auto load_B = [&](int tl, int buf) {
+        const int g = P.g0 + tl;
+        const int nR = P.minu_n[g];
+        if (nR <= 0) return;
+        const int np = (nR + 3) & ~3;
+        const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * P.minu_off[g]);
+        float4* dst = reinterpret_cast<float4*>(B + (size_t)buf * P.b_buf_stride);
+        for (int e = tid; e < 24 * np; e += kSimThreads) cp_async16(dst + e, src + e);
+    };
+    auto load_A = [&](int q) {
+        for (int s = 0; s < 3; ++s) {
+            const int nL = P.slot_n[q * 3 + s];
+            if (nL <= 0) continue;
+            const int np = (nL + 3) & ~3;
+            const float4* src = reinterpret_cast<const float4*>(P.lat_desT + (size_t)96 * P.slot_off[q * 3 + s]);
+            float4* dst = reinterpret_cast<float4*>(A + (size_t)s * P.a_slot_stride);
+            for (int e = tid; e < 24 * np; e += kSimThreads) cp_async16(dst + e, src + e);
+        }
+    };
+
+    int tl = blockIdx.x;
+    if (tl >= P.n_chunk) return;
+    load_B(tl, 0);
+    if (P.Q == 1) load_A(0);
+    cp_async_commit();
+
+    for (int it = 0; tl < P.n_chunk; tl += gridDim.x, ++it) {
+        const int cur = P.b_double ? (it & 1) : 0;
+        const int tl_next = tl + gridDim.x;
+        bool prefetched = false;
+        if (P.b_double && tl_next < P.n_chunk) {
+            load_B(tl_next, cur ^ 1);
+            prefetched = true;
+        }
+        cp_async_commit();
+        const int g = P.g0 + tl;
+        const int nR = P.minu_n[g];
+        const int npR = (nR + 3) & ~3;
+        const float* Bt = B + (size_t)cur * P.b_buf_stride;
+        const int tiles_j = (nR + 127) >> 7;
+
+        for (int q = 0; q < P.Q; ++q) {
+            const bool live = P.lat_status[q] == 0 && nR > 0;
+            if (P.Q > 1) {
+                __syncthreads();  // previous latent's tiles are done with A
+                if (live) load_A(q);
+                cp_async_commit();
+                cp_async_wait<0>();
+            } else {
+                if (prefetched) cp_async_wait<1>();
+                else cp_async_wait<0>();
+            }
+            __syncthreads();
+            if (!live) continue;
+
+            // tile list over the three slots.  A warp tile is 16 rows x 16*NC columns (8 x NC per thread); templates
+            // of up to 160 minutiae are spanned by ONE tile of the smallest sufficient width, larger ones by
+            // 128-column tiles.
+            const int nc = nR <= 160 ? max(6, (nR + 15) >> 4) : 8;
+            const int tiles_jj = nR <= 160 ? 1 : tiles_j;
+            int t0[4];
+            t0[0] = 0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_jj;
+            for (int t = warp; t < t0[3]; t += NW) {
+                const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
+                const int tt = t - t0[s];
+                const int ti = tt / tiles_jj, tj = tt - ti * tiles_jj;
+                const int nL = P.slot_n[q * 3 + s];
+                const int npL = (nL + 3) & ~3;
+                const int i0 = ti * 16 + li * 8;
+                const float* ap = A + (size_t)s * P.a_slot_stride + i0;
+                float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
+                switch (nc) {
+                    case 6: sim_tile<6>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 7: sim_tile<7>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 9: sim_tile<9>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    case 10: sim_tile<10>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
+                    default: sim_tile<8>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out); break;
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this gallery block before it is overwritten
+        if (!P.b_double && tl_next < P.n_chunk) {
+            load_B(tl_next, 0);
+            cp_async_commit();
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// The same tiles scheduled as jobs = (latent, part of the chunk): the latent's blocks are staged once per job instead
+// of once per (template, latent), and the job count is a multiple of the grid.  Measured: better when a batch leaves
+// only a few templates per CTA and chunk (256 latents, 620-template chunks: 1,474 -> 1,261 ms per 5.1 M pairs), slightly
+// worse otherwise (23.6 against 23.3 ms for a single latent, 24.7 against 24.0 ms per latent for 27) - the host picks.
+__global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* A = reinterpret_cast<float*>(smem);        // [3][a_slot_stride]
     float* B = A + 3 * (size_t)P.a_slot_stride;       // [1|2][b_buf_stride]
