@@ -197,6 +197,28 @@ LAFIS_API void lafis_forget_gallery_dir(lafis_ctx* ctx);
  *      pointers when on_device != 0. ---- */
 LAFIS_API int lafis_pq_encode(lafis_ctx* ctx, const float* des, int64_t n, uint8_t* codes, int on_device);
 
+/* ---- descriptor compression 192 -> 96: the reference's CompNet in eval mode
+ *      (extraction/models/net_compress.py:33-53, BasicBlock :7-31) as run by template_compression
+ *      (extraction/descriptor_DR.py:141-152), including the re-normalisation row / ||row|| * 1.73 (:150-152).
+ *      The reference ships no weights: the caller passes the state_dict tensors (torch layouts, fp32) of
+ *      layer l = 0..3 = layer1.0/.1, layer2.layers.0/.1, layer2.layers.3/.4, layer3.0/.1 —
+ *      weight[l] is the Linear weight [96][192] (l = 0) or [96][96], bias[l] its bias [96], bn_*[l] the
+ *      BatchNorm1d parameters / running statistics [96].  Host pointers; the network stays resident on the
+ *      context.  lafis_compress_descriptors maps des_in [n][192] to des_out [n][96] (device pointers when
+ *      on_device != 0; 16-byte aligned); normalise = 0 returns the raw network output. ---- */
+typedef struct {
+    const float* weight[4];
+    const float* bias[4];
+    const float* bn_weight[4];
+    const float* bn_bias[4];
+    const float* bn_mean[4];
+    const float* bn_var[4];
+    float bn_eps; /* torch default 1e-5 */
+} lafis_compnet_weights;
+LAFIS_API int lafis_compnet_load(lafis_ctx* ctx, const lafis_compnet_weights* w);
+LAFIS_API int lafis_compress_descriptors(lafis_ctx* ctx, const float* des_in, int64_t n, float* des_out, int normalise,
+                                         int on_device);
+
 /* ---- enrollment of one rolled print: the tail of the reference's extraction pipeline,
  *      TrainedPQEncoder.encode_multi (descriptor_PQ.py:19-27) on the texture descriptors followed by
  *      Template2Bin_Byte_PQ_rolled (:178-272).  Coordinates arrive as the reference holds them, rows of
@@ -211,6 +233,9 @@ typedef struct {
     int n_tex;
     const float* tex_xyo;     /* [n_tex][3], pixels */
     const float* tex_des;     /* [n_tex][96], PQ-encoded on the device */
+    int des_len;              /* 96 (or 0): descriptors are final.  192: raw descriptors; minutiae and texture
+                                 descriptors first go through lafis_compress_descriptors on the device
+                                 (needs lafis_compnet_load), arrays are then [n][192] */
 } lafis_rolled_features;
 LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* features, const char* out_path);
 

@@ -163,7 +163,21 @@ LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* F
         minu.y[i] = (int16_t)(uint16_t)F->minu_xyo[3 * i + 1];
         minu.ori[i] = F->minu_xyo[3 * i + 2];
     }
-    minu.des.assign(F->minu_des, F->minu_des + (size_t)nm * kDesLen);
+    // raw 192-d descriptors: CompNet + re-normalisation first (descriptor_DR.py:141-165)
+    if (F->des_len != 0 && F->des_len != kDesLen && F->des_len != 2 * kDesLen) return LAFIS_ERR_ARG;
+    const bool raw = F->des_len == 2 * kDesLen;
+    std::vector<float> tex_small;
+    const float* tex_des = F->tex_des;
+    if (raw) {
+        minu.des.resize((size_t)nm * kDesLen);
+        tex_small.resize((size_t)nt * kDesLen);
+        int rc = nm > 0 ? lafis_compress_descriptors(ctx, F->minu_des, nm, minu.des.data(), 1, 0) : LAFIS_OK;
+        if (rc == LAFIS_OK && nt > 0) rc = lafis_compress_descriptors(ctx, F->tex_des, nt, tex_small.data(), 1, 0);
+        if (rc != LAFIS_OK) return rc;
+        tex_des = tex_small.data();
+    } else {
+        minu.des.assign(F->minu_des, F->minu_des + (size_t)nm * kDesLen);
+    }
     tex.x.resize(nt);
     tex.y.resize(nt);
     tex.ori.resize(nt);
@@ -174,7 +188,7 @@ LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* F
     }
     tex.codes.resize((size_t)nt * kSubs);
     if (nt > 0) {
-        const int rc = lafis_pq_encode(ctx, F->tex_des, nt, tex.codes.data(), 0);
+        const int rc = lafis_pq_encode(ctx, tex_des, nt, tex.codes.data(), 0);
         if (rc != LAFIS_OK) return rc;
     }
     return write_rolled_dat(out_path, F->h, F->w, F->blkH, F->blkW, minu, tex) == 0 ? LAFIS_OK : LAFIS_ERR_IO;

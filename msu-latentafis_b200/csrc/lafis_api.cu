@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/latentafis_b200.h"
+#include "compnet.cuh"
 #include "dat_format.h"
 #include "device_common.cuh"
 #include "graph_prune.cuh"
@@ -100,6 +101,7 @@ struct lafis_ctx {
 
     float* d_codebook = nullptr;  // [16][256][6]
     float* d_table = nullptr;     // [50*50]
+    float* d_compnet = nullptr;   // CompNet: k-major weights [46080] + folded BatchNorm scale/shift [4][2][96]
 
     // gallery
     DeviceGallery gal;
@@ -235,6 +237,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
                                  (int)sizeof(SparseWork<false>)));
         TRY(cudaFuncSetAttribute(graph_tex_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SparseWork<true>)));
+        TRY(cudaFuncSetAttribute(compnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compnet_smem_bytes()));
     }
 #undef TRY
     if (!ok) {
@@ -307,6 +310,7 @@ void lafis_destroy(lafis_ctx* c) {
     c->lat_arena.release();
     cudaFree(c->d_codebook);
     cudaFree(c->d_table);
+    cudaFree(c->d_compnet);
     cudaFree(c->d_job_counter);
     cudaFree(c->d_slow);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1385,6 +1389,79 @@ int lafis_pq_encode(lafis_ctx* c, const float* des, int64_t n, uint8_t* codes, i
     cudaFree(tmp_codes);
     if (e != cudaSuccess || e2 != cudaSuccess)
         return fail(c, LAFIS_ERR_CUDA, "pq_encode failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return LAFIS_OK;
+}
+
+int lafis_compnet_load(lafis_ctx* c, const lafis_compnet_weights* w) {
+    if (!c || !w) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    for (int l = 0; l < 4; ++l)
+        if (!w->weight[l] || !w->bias[l] || !w->bn_weight[l] || !w->bn_bias[l] || !w->bn_mean[l] || !w->bn_var[l])
+            return fail(c, LAFIS_ERR_ARG, "CompNet layer %d: missing tensor", l);
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    // k-major copies of the torch [out][in] weights; Linear bias and eval-mode BatchNorm1d
+    // ((v - mean) / sqrt(var + eps) * gamma + beta) folded into one scale and shift per output
+    std::vector<float> h((size_t)kCompWeightFloats + kCompAffFloats);
+    size_t off = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int in = l == 0 ? kCompIn : kCompOut;
+        for (int k = 0; k < in; ++k)
+            for (int o = 0; o < kCompOut; ++o) h[off + (size_t)k * kCompOut + o] = w->weight[l][(size_t)o * in + k];
+        off += (size_t)in * kCompOut;
+    }
+    for (int l = 0; l < 4; ++l)
+        for (int o = 0; o < kCompOut; ++o) {
+            const double scale = (double)w->bn_weight[l][o] / std::sqrt((double)w->bn_var[l][o] + (double)w->bn_eps);
+            h[off + (size_t)(l * 2 + 0) * kCompOut + o] = (float)scale;
+            h[off + (size_t)(l * 2 + 1) * kCompOut + o] =
+                (float)(((double)w->bias[l][o] - (double)w->bn_mean[l][o]) * scale + (double)w->bn_bias[l][o]);
+        }
+    if (!c->d_compnet) LAFIS_CUDA(c, cudaMalloc(&c->d_compnet, sizeof(float) * h.size()));
+    LAFIS_CUDA(c, cudaMemcpyAsync(c->d_compnet, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LAFIS_OK;
+}
+
+int lafis_compress_descriptors(lafis_ctx* c, const float* des_in, int64_t n, float* des_out, int normalise,
+                               int on_device) {
+    if (!c || !des_in || !des_out || n < 0) return fail(c, LAFIS_ERR_ARG, "bad argument");
+    if (!c->d_compnet) return fail(c, LAFIS_ERR_ARG, "lafis_compnet_load has not been called on this context");
+    if (on_device && (((uintptr_t)des_in | (uintptr_t)des_out) & 15u))
+        return fail(c, LAFIS_ERR_ARG, "device descriptors must be 16-byte aligned");
+    if (n == 0) return LAFIS_OK;
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    const float* d_in = des_in;
+    float* d_out = des_out;
+    float* tmp_in = nullptr;
+    float* tmp_out = nullptr;
+    if (!on_device) {
+        LAFIS_CUDA(c, cudaMalloc(&tmp_in, sizeof(float) * kCompIn * (size_t)n));
+        if (cudaMalloc(&tmp_out, sizeof(float) * kCompOut * (size_t)n) != cudaSuccess) {
+            cudaFree(tmp_in);
+            return fail(c, LAFIS_ERR_CUDA, "cudaMalloc failed");
+        }
+        cudaMemcpyAsync(tmp_in, des_in, sizeof(float) * kCompIn * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        d_in = tmp_in;
+        d_out = tmp_out;
+    }
+    CompNetParams P;
+    P.x = d_in;
+    P.n = (long long)n;
+    P.out = d_out;
+    P.wt = c->d_compnet;
+    P.aff = c->d_compnet + kCompWeightFloats;
+    P.normalise = normalise;
+    const long long groups = (n + kCompPts - 1) / kCompPts;
+    const unsigned grid = (unsigned)std::min<long long>(c->sm_count, (groups + kCompWarps - 1) / kCompWarps);
+    compnet_kernel<<<grid, kCompWarps * 32, compnet_smem_bytes(), c->stream>>>(P);
+    c->stats.kernel_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !on_device)
+        e = cudaMemcpyAsync(des_out, tmp_out, sizeof(float) * kCompOut * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp_in);
+    cudaFree(tmp_out);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(c, LAFIS_ERR_CUDA, "compress_descriptors failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     return LAFIS_OK;
 }
 

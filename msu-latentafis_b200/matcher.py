@@ -61,7 +61,13 @@ class _PackedLatents(C.Structure):
 class _RolledFeatures(C.Structure):
     _fields_ = [("h", C.c_int), ("w", C.c_int), ("blkH", C.c_int), ("blkW", C.c_int), ("n_minu", C.c_int),
                 ("minu_xyo", C.c_void_p), ("minu_des", C.c_void_p), ("n_tex", C.c_int), ("tex_xyo", C.c_void_p),
-                ("tex_des", C.c_void_p)]
+                ("tex_des", C.c_void_p), ("des_len", C.c_int)]
+
+
+class _CompNetWeights(C.Structure):
+    _fields_ = [("weight", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("bn_weight", C.c_void_p * 4),
+                ("bn_bias", C.c_void_p * 4), ("bn_mean", C.c_void_p * 4), ("bn_var", C.c_void_p * 4),
+                ("bn_eps", C.c_float)]
 
 
 class _Stats(C.Structure):
@@ -81,7 +87,7 @@ EXPORTS = [
     "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device",
     "lafis_correspondences", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
-    "lafis_enroll_rolled",
+    "lafis_enroll_rolled", "lafis_compnet_load", "lafis_compress_descriptors",
     "lafis_get_stats", "lafis_set_streams", "lafis_stream",
 ]
 
@@ -133,6 +139,8 @@ def load_library():
     L.lafis_forget_gallery_dir.restype = None
     L.lafis_pq_encode.argtypes = [vp, vp, C.c_int64, vp, ci]
     L.lafis_enroll_rolled.argtypes = [vp, C.POINTER(_RolledFeatures), cp]
+    L.lafis_compnet_load.argtypes = [vp, C.POINTER(_CompNetWeights)]
+    L.lafis_compress_descriptors.argtypes = [vp, vp, C.c_int64, vp, ci, ci]
     L.lafis_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.lafis_set_streams.argtypes = [vp, ci]
     L.lafis_stream.argtypes = [vp]
@@ -287,6 +295,28 @@ class Latents:
             pass
 
 
+def compnet_layers(state):
+    """CompNet state_dict (ordered mapping name -> array, or a sequence of arrays in state_dict order) ->
+    4 dicts {weight, bias, bn_weight, bn_bias, bn_mean, bn_var}, one per Linear + BatchNorm1d pair:
+    layer1.0/.1, layer2.layers.0/.1, layer2.layers.3/.4, layer3.0/.1 (net_compress.py:10-17, :40-50)."""
+    vals = list(state.values()) if hasattr(state, "values") else list(state)
+    arrs = []
+    for v in vals:
+        a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+        if a.ndim == 0:  # BatchNorm1d.num_batches_tracked
+            continue
+        arrs.append(a.astype(np.float32))
+    if len(arrs) != 24:
+        raise ValueError(f"CompNet state has {len(arrs)} tensors, expected 24")
+    names = ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var")
+    layers = [dict(zip(names, arrs[6 * l:6 * l + 6])) for l in range(4)]
+    for l, L in enumerate(layers):
+        want = (96, 192) if l == 0 else (96, 96)
+        if L["weight"].shape != want or any(L[k].shape != (96,) for k in names[1:]):
+            raise ValueError(f"CompNet layer {l}: unexpected tensor shapes")
+    return layers
+
+
 class Matcher:
     """`PQ::Matcher` (matching/matcher.h:34-52) on one B200."""
 
@@ -432,12 +462,47 @@ class Matcher:
         self._chk(self.L.lafis_pq_encode(self.ctx, int(des), int(n), int(codes_ptr), 1))
         return None
 
+    def load_compnet(self, state) -> None:
+        """Make the descriptor-compression network resident (lafis_compnet_load).  `state` is the CompNet
+        state_dict (extraction/models/net_compress.py:33-53) as an ordered mapping or sequence of arrays in
+        state_dict order - mapped by POSITION like the reference's load_model (descriptor_DR.py:39-46);
+        num_batches_tracked entries are skipped."""
+        arrs = compnet_layers(state)
+        W = _CompNetWeights()
+        keep = []
+        for l, layer in enumerate(arrs):
+            for name in ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var"):
+                a = np.ascontiguousarray(layer[name], np.float32)
+                keep.append(a)
+                getattr(W, name)[l] = a.ctypes.data
+        W.bn_eps = 1e-5
+        self._chk(self.L.lafis_compnet_load(self.ctx, C.byref(W)))
+
+    def compress_descriptors(self, des, n: Optional[int] = None, out_ptr: Optional[int] = None, normalise: bool = True):
+        """CompNet 192 -> 96 + normalisation to 1.73 (descriptor_DR.py:141-152).  numpy [n,192] -> numpy [n,96];
+        or raw device pointers (des, n, out_ptr)."""
+        if isinstance(des, np.ndarray):
+            d = np.ascontiguousarray(des, np.float32)
+            if d.ndim != 2 or d.shape[1] != 192:
+                raise ValueError("descriptors must be [n, 192]")
+            out = np.zeros((d.shape[0], 96), np.float32)
+            self._chk(self.L.lafis_compress_descriptors(self.ctx, _ptr(d), d.shape[0], _ptr(out), int(normalise), 0))
+            return out
+        self._chk(self.L.lafis_compress_descriptors(self.ctx, int(des), int(n), int(out_ptr), int(normalise), 1))
+        return None
+
     def enroll_rolled(self, out_path: str, minu_xyo, minu_des, tex_xyo, tex_des, h: int = 800, w: int = 768,
                       blkH: int = 50, blkW: int = 48) -> None:
         """Tail of the reference's enrollment (descriptor_PQ.py:19-27 + :178-272): PQ-encodes the texture
-        descriptors on the GPU and writes the rolled template file.  *_xyo: [n, 3] rows of x, y (pixels), orientation."""
+        descriptors on the GPU and writes the rolled template file.  *_xyo: [n, 3] rows of x, y (pixels), orientation.
+        192-d descriptors are first compressed by the resident CompNet (descriptor_DR.py:141-165)."""
         a = [np.ascontiguousarray(v, np.float32) for v in (minu_xyo, minu_des, tex_xyo, tex_des)]
-        F = _RolledFeatures(h, w, blkH, blkW, len(a[0]), _ptr(a[0]), _ptr(a[1]), len(a[2]), _ptr(a[2]), _ptr(a[3]))
+        des_len = 96
+        for d in (a[1], a[3]):
+            if d.size:
+                des_len = int(d.shape[1])
+        F = _RolledFeatures(h, w, blkH, blkW, len(a[0]), _ptr(a[0]), _ptr(a[1]), len(a[2]), _ptr(a[2]), _ptr(a[3]),
+                            des_len)
         self._chk(self.L.lafis_enroll_rolled(self.ctx, C.byref(F), out_path.encode()))
 
     def stats(self) -> dict:
