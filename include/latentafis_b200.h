@@ -239,6 +239,28 @@ typedef struct {
 } lafis_rolled_features;
 LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* features, const char* out_path);
 
+/* ---- enrollment of one latent print: Template2Bin_Byte_latent (extraction/descriptor_PQ.py:80-175), the writer
+ *      of the files lafis_latents_load_files / the reference's load_FP_template(latent) read.  The reference
+ *      pipeline produces 28 minutiae templates and one texture template; all are written in order (an empty
+ *      minutiae template is written as its zero count, :113-117, and shifts the reader's template indices as in
+ *      matcher.cpp:834-836).  Coordinates as in lafis_rolled_features: {x, y, orientation} rows in pixels,
+ *      texture points are written in block units.  des_len 192: every descriptor of the print goes through
+ *      lafis_compress_descriptors in ONE device call first (descriptor_DR.py:196-230). ---- */
+typedef struct {
+    int n;             /* points; at most 2000 are written */
+    const float* xyo;  /* [n][3] */
+    const float* des;  /* [n][des_len] */
+} lafis_point_set;
+typedef struct {
+    int h, w, blkH, blkW;
+    int n_minu_templates;         /* <= 255 */
+    const lafis_point_set* minu;  /* [n_minu_templates] */
+    int n_tex_templates;          /* <= 255 */
+    const lafis_point_set* tex;   /* [n_tex_templates] */
+    int des_len;                  /* 96 (or 0), or 192 (needs lafis_compnet_load) */
+} lafis_latent_features;
+LAFIS_API int lafis_enroll_latent(lafis_ctx* ctx, const lafis_latent_features* features, const char* out_path);
+
 /* ---- instrumentation ---- */
 typedef struct {
     uint64_t kernel_launches; /* kernels launched by this library since the context was created */

@@ -250,6 +250,52 @@ int write_rolled_dat(const std::string& path, int h, int w, int blkH, int blkW, 
     return ok ? 0 : -3;
 }
 
+int write_latent_dat(const std::string& path, int h, int w, int blkH, int blkW, const std::vector<PointSet>& minu,
+                     const std::vector<PointSet>& tex) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return -3;
+    bool ok = true;
+    auto put = [&](const void* p, size_t bytes) {
+        if (bytes) ok = ok && std::fwrite(p, 1, bytes, f) == bytes;
+    };
+    auto put_u16 = [&](unsigned v) {
+        const uint16_t x = (uint16_t)v;
+        put(&x, 2);
+    };
+    auto put_u8 = [&](unsigned v) {
+        const uint8_t x = (uint8_t)v;
+        put(&x, 1);
+    };
+    uint16_t header[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // descriptor_PQ.py:87-91
+    put(header, sizeof header);
+    if (minu.empty()) {  // :92-95 "empty" file
+        uint16_t zeros[4] = {0, 0, 0, 0};
+        put(zeros, sizeof zeros);
+        ok = (std::fclose(f) == 0) && ok;
+        return ok ? 0 : -3;
+    }
+    put_u16((unsigned)h);
+    put_u16((unsigned)w);
+    put_u16((unsigned)std::min(blkH, 50));
+    put_u16((unsigned)std::min(blkW, 50));
+    auto put_set = [&](const PointSet& s) {
+        const int n = std::min(s.n(), kMaxMinutiae);
+        put_u16((unsigned)n);
+        if (n <= 0) return;
+        put(s.x.data(), 2 * (size_t)n);
+        put(s.y.data(), 2 * (size_t)n);
+        put(s.ori.data(), 4 * (size_t)n);
+        put_u16(kDesLen);
+        put(s.des.data(), 4 * (size_t)n * kDesLen);
+    };
+    put_u8((unsigned)minu.size());
+    for (const PointSet& s : minu) put_set(s);
+    put_u8((unsigned)tex.size());
+    for (const PointSet& s : tex) put_set(s);
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? 0 : -3;
+}
+
 int read_codebook(const std::string& path, std::vector<float>& cw, int& subs, int& clusters, int& sub_dim) {
     std::vector<uint8_t> buf;
     if (!slurp(path, buf)) return -3;

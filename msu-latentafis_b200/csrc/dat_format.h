@@ -51,6 +51,13 @@ int read_latent_dat(const std::string& path, LatentTemplate& out);
 // are written (:213-214, :245-246).  Returns 0, or -3 on I/O error.
 int write_rolled_dat(const std::string& path, int h, int w, int blkH, int blkW, const PointSet& minu, const PointSet& tex);
 
+// Writes a latent template in the layout of Template2Bin_Byte_latent (extraction/descriptor_PQ.py:80-175): version-1
+// header, h, w, block sizes clamped to 50, `minu.size()` minutiae templates (an empty one is just its zero count,
+// :113-117) and `tex.size()` texture templates with block coordinates and f32 descriptors [n][96].  At most 2000
+// points per template are written (:111-112, :143-144).  Returns 0, or -3 on I/O error.
+int write_latent_dat(const std::string& path, int h, int w, int blkH, int blkW, const std::vector<PointSet>& minu,
+                     const std::vector<PointSet>& tex);
+
 // u16 subs, u16 clusters, u16 sub_dim, f32[subs][clusters][sub_dim]; returns 0 or a negative LAFIS_ERR_*
 int read_codebook(const std::string& path, std::vector<float>& codewords, int& subs, int& clusters, int& sub_dim);
 

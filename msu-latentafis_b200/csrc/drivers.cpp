@@ -194,6 +194,57 @@ LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* F
     return write_rolled_dat(out_path, F->h, F->w, F->blkH, F->blkW, minu, tex) == 0 ? LAFIS_OK : LAFIS_ERR_IO;
 }
 
+LAFIS_API int lafis_enroll_latent(lafis_ctx* ctx, const lafis_latent_features* F, const char* out_path) {
+    if (!ctx || !F || !out_path || F->n_minu_templates < 0 || F->n_minu_templates > 255 || F->n_tex_templates < 0 ||
+        F->n_tex_templates > 255 || (F->n_minu_templates > 0 && !F->minu) || (F->n_tex_templates > 0 && !F->tex))
+        return LAFIS_ERR_ARG;
+    if (F->des_len != 0 && F->des_len != kDesLen && F->des_len != 2 * kDesLen) return LAFIS_ERR_ARG;
+    const int in_len = F->des_len == 2 * kDesLen ? 2 * kDesLen : kDesLen;
+    const int nmt = F->n_minu_templates, ntt = F->n_tex_templates;
+    std::vector<PointSet> sets(nmt + ntt);
+    std::vector<float> raw;  // 192-d descriptors of the whole print, template after template
+    size_t total = 0;
+    for (int t = 0; t < nmt + ntt; ++t) {
+        const lafis_point_set& in = t < nmt ? F->minu[t] : F->tex[t - nmt];
+        if (in.n < 0 || (in.n > 0 && (!in.xyo || !in.des))) return LAFIS_ERR_ARG;
+        total += (size_t)std::min(in.n, kMaxMinutiae);
+    }
+    if (in_len != kDesLen) raw.reserve(total * in_len);
+    for (int t = 0; t < nmt + ntt; ++t) {
+        const bool is_tex = t >= nmt;
+        const lafis_point_set& in = is_tex ? F->tex[t - nmt] : F->minu[t];
+        PointSet& s = sets[t];
+        const int n = std::min(in.n, kMaxMinutiae);
+        s.x.resize(n);
+        s.y.resize(n);
+        s.ori.resize(n);
+        for (int i = 0; i < n; ++i) {
+            if (is_tex) {  // block units (descriptor_PQ.py:149-156)
+                s.x[i] = (int16_t)(uint16_t)((in.xyo[3 * i] - 24.0f) / 16.0f);
+                s.y[i] = (int16_t)(uint16_t)((in.xyo[3 * i + 1] - 24.0f) / 16.0f);
+            } else {  // np.uint16(x): truncation (:118-123)
+                s.x[i] = (int16_t)(uint16_t)in.xyo[3 * i];
+                s.y[i] = (int16_t)(uint16_t)in.xyo[3 * i + 1];
+            }
+            s.ori[i] = in.xyo[3 * i + 2];
+        }
+        if (in_len == kDesLen) s.des.assign(in.des, in.des + (size_t)n * kDesLen);
+        else raw.insert(raw.end(), in.des, in.des + (size_t)n * in_len);
+    }
+    if (in_len != kDesLen && total > 0) {
+        std::vector<float> small(total * kDesLen);
+        const int rc = lafis_compress_descriptors(ctx, raw.data(), (int64_t)total, small.data(), 1, 0);
+        if (rc != LAFIS_OK) return rc;
+        size_t at = 0;
+        for (PointSet& s : sets) {
+            s.des.assign(small.begin() + at * kDesLen, small.begin() + (at + s.n()) * kDesLen);
+            at += s.n();
+        }
+    }
+    const std::vector<PointSet> minu(sets.begin(), sets.begin() + nmt), tex(sets.begin() + nmt, sets.end());
+    return write_latent_dat(out_path, F->h, F->w, F->blkH, F->blkW, minu, tex) == 0 ? LAFIS_OK : LAFIS_ERR_IO;
+}
+
 LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
                                        const char* score_path) {
     if (!ctx || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;

@@ -82,4 +82,20 @@ int hc_rolled_arrays(const char* path, short* mx, short* my, float* mori, float*
     cp(codes, R.tex.codes.data(), R.tex.codes.size());
     return rc;
 }
+// write_latent_dat from flat arrays: counts[t] points per template (minutiae templates first), arrays concatenated
+int hc_write_latent(const char* path, int h, int w, int blkH, int blkW, int n_minu_t, int n_tex_t, const int* counts,
+                    const short* x, const short* y, const float* ori, const float* des) {
+    std::vector<PointSet> minu(n_minu_t), tex(n_tex_t);
+    size_t at = 0;
+    for (int t = 0; t < n_minu_t + n_tex_t; ++t) {
+        PointSet& s = t < n_minu_t ? minu[t] : tex[t - n_minu_t];
+        const size_t n = (size_t)counts[t];
+        s.x.assign(x + at, x + at + n);
+        s.y.assign(y + at, y + at + n);
+        s.ori.assign(ori + at, ori + at + n);
+        s.des.assign(des + at * kDesLen, des + (at + n) * kDesLen);
+        at += n;
+    }
+    return write_latent_dat(path, h, w, blkH, blkW, minu, tex);
+}
 }

@@ -64,6 +64,16 @@ class _RolledFeatures(C.Structure):
                 ("tex_des", C.c_void_p), ("des_len", C.c_int)]
 
 
+class _PointSet(C.Structure):
+    _fields_ = [("n", C.c_int), ("xyo", C.c_void_p), ("des", C.c_void_p)]
+
+
+class _LatentFeatures(C.Structure):
+    _fields_ = [("h", C.c_int), ("w", C.c_int), ("blkH", C.c_int), ("blkW", C.c_int), ("n_minu_templates", C.c_int),
+                ("minu", C.POINTER(_PointSet)), ("n_tex_templates", C.c_int), ("tex", C.POINTER(_PointSet)),
+                ("des_len", C.c_int)]
+
+
 class _CompNetWeights(C.Structure):
     _fields_ = [("weight", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("bn_weight", C.c_void_p * 4),
                 ("bn_bias", C.c_void_p * 4), ("bn_mean", C.c_void_p * 4), ("bn_var", C.c_void_p * 4),
@@ -87,7 +97,7 @@ EXPORTS = [
     "lafis_latents_free", "lafis_latents_make_resident", "lafis_latents_bytes", "lafis_match", "lafis_match_device",
     "lafis_correspondences", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
-    "lafis_enroll_rolled", "lafis_compnet_load", "lafis_compress_descriptors",
+    "lafis_enroll_rolled", "lafis_enroll_latent", "lafis_compnet_load", "lafis_compress_descriptors",
     "lafis_get_stats", "lafis_set_streams", "lafis_stream",
 ]
 
@@ -139,6 +149,7 @@ def load_library():
     L.lafis_forget_gallery_dir.restype = None
     L.lafis_pq_encode.argtypes = [vp, vp, C.c_int64, vp, ci]
     L.lafis_enroll_rolled.argtypes = [vp, C.POINTER(_RolledFeatures), cp]
+    L.lafis_enroll_latent.argtypes = [vp, C.POINTER(_LatentFeatures), cp]
     L.lafis_compnet_load.argtypes = [vp, C.POINTER(_CompNetWeights)]
     L.lafis_compress_descriptors.argtypes = [vp, vp, C.c_int64, vp, ci, ci]
     L.lafis_get_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -504,6 +515,29 @@ class Matcher:
         F = _RolledFeatures(h, w, blkH, blkW, len(a[0]), _ptr(a[0]), _ptr(a[1]), len(a[2]), _ptr(a[2]), _ptr(a[3]),
                             des_len)
         self._chk(self.L.lafis_enroll_rolled(self.ctx, C.byref(F), out_path.encode()))
+
+    def enroll_latent(self, out_path: str, minu_sets, tex_sets, h: int = 800, w: int = 768, blkH: int = 50,
+                      blkW: int = 48) -> None:
+        """Template2Bin_Byte_latent (descriptor_PQ.py:80-175): minu_sets / tex_sets are sequences of (xyo [n,3], des [n,L])
+        pairs in template order, L = 96, or 192 (compressed by the resident CompNet in one device call)."""
+        keep = []
+        des_len = 96
+
+        def pack(sets):
+            nonlocal des_len
+            arr = (_PointSet * max(len(sets), 1))()
+            for t, (xyo, des) in enumerate(sets):
+                a = np.ascontiguousarray(xyo, np.float32).reshape(-1, 3)
+                d = np.ascontiguousarray(des, np.float32)
+                if d.size:
+                    des_len = int(d.shape[1])
+                keep.extend([a, d])
+                arr[t] = _PointSet(len(a), _ptr(a), _ptr(d))
+            return arr
+
+        ma, ta = pack(list(minu_sets)), pack(list(tex_sets))
+        F = _LatentFeatures(h, w, blkH, blkW, len(minu_sets), ma, len(tex_sets), ta, des_len)
+        self._chk(self.L.lafis_enroll_latent(self.ctx, C.byref(F), out_path.encode()))
 
     def stats(self) -> dict:
         s = _Stats()

@@ -99,3 +99,43 @@ def test_parser_limits_and_short_files(pkg, hc, tmp_path):
     open(p, "wb").write(hdr + struct.pack("<B", 0) + struct.pack("<B", 1) + struct.pack("<h", 2001))
     assert _rolled_counts(hc, p)[0] == -1 and _latent_counts(hc, p)[0] == -1
     assert _rolled_counts(hc, str(tmp_path / "missing.dat"))[0] == -3
+
+
+def _hc_write_latent(hc, path, lat):
+    sets = list(lat.minu) + list(lat.tex)
+    counts = np.array([s.n for s in sets], np.int32)
+    cat = lambda f, dt, w=None: np.ascontiguousarray(np.concatenate([np.asarray(f(s), dt).reshape((-1,) if w is None else (-1, w)) for s in sets]))
+    x, y, ori, des = cat(lambda s: s.x, np.int16), cat(lambda s: s.y, np.int16), cat(lambda s: s.ori, np.float32), \
+        cat(lambda s: s.des, np.float32, 96)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    return hc.hc_write_latent(path.encode(), lat.h, lat.w, lat.blkH, lat.blkW, len(lat.minu), len(lat.tex), vp(counts), vp(x),
+                              vp(y), vp(ori), vp(des))
+
+
+def test_latent_writer_is_byte_identical_to_the_python_writer(pkg, hc, tmp_path):
+    """write_latent_dat (csrc/dat_format.cpp) against templates.write_template, i.e. the layout of
+    Template2Bin_Byte_latent (descriptor_PQ.py:80-175), including an empty minutiae template in the middle, and the
+    reference's own loader accepting the file when oracle/_ref is present."""
+    T = pkg.templates
+    raw = T.synth_rolled_raw(12, n_minu=50, n_tex=120)
+    lat = T.synth_latent(3, raw, n_minu=17, n_tex_pts=40)
+    lat.blkH = 77  # clamped to 50 by the writer
+    a, b = str(tmp_path / "c.dat"), str(tmp_path / "py.dat")
+    assert _hc_write_latent(hc, a, lat) == 0
+    T.write_template(b, lat)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    rc, nm, nt, slots, ntex = _latent_counts(hc, a)
+    assert (rc, nm, nt, slots, ntex) == (0, 28, 1, [17, 17, 17], 80)
+    lat.minu[4] = T.MinutiaeTemplate(np.zeros(0, np.int16), np.zeros(0, np.int16), np.zeros(0, np.float32),
+                                     np.zeros((0, 96), np.float32))
+    assert _hc_write_latent(hc, a, lat) == 0
+    T.write_template(b, lat)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    import refbind
+    if refbind.available():
+        cbp = str(tmp_path / "cb.dat")
+        T.write_codebook(cbp, T.synthetic_codebook())
+        R = refbind.RefMatcher(cbp)
+        _, rc = R.load_latent(a)
+        assert rc == 0
+        R.close()

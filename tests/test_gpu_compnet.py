@@ -117,3 +117,29 @@ def test_enroll_rolled_from_raw_descriptors(pkg, matcher, golden, golden_compnet
     assert np.array_equal(got.tex[0].des, matcher.pq_encode(gpu_tex))
     same = got.tex[0].des == T.pq_encode(want_tex, cb)
     assert same.mean() > 0.999  # a 1e-6 perturbation flips a nearest centroid only at a near-tie
+
+
+def test_enroll_latent_from_raw_descriptors(pkg, matcher, golden_compnet, tmp_path):
+    """28 minutiae templates + 1 texture template of 192-d descriptors -> one device call -> latent .dat whose
+    descriptors are the oracle's compressed ones (tolerance as above), template after template."""
+    import compnet_oracle as co
+    T = pkg.templates
+    rng = np.random.default_rng(5)
+    sizes = [int(rng.integers(0, 60)) for _ in range(28)]
+    sizes[3] = 0  # an empty minutiae template: written as its zero count, skipped by the readers
+    minu_sets = [(np.stack([rng.integers(40, 700, n), rng.integers(40, 700, n), rng.uniform(-3, 3, n)], 1).astype(np.float32),
+                  rng.standard_normal((n, 192)).astype(np.float32)) for n in sizes]
+    nt = 180
+    tex_sets = [(np.stack([24 + 16 * rng.integers(0, 40, nt), 24 + 16 * rng.integers(0, 40, nt), rng.uniform(-1.5, 1.5, nt)], 1).astype(np.float32),
+                 rng.standard_normal((nt, 192)).astype(np.float32))]
+    p = os.path.join(str(tmp_path), "lat192.dat")
+    matcher.enroll_latent(p, minu_sets, tex_sets)
+    got = T.read_template(p, latent=True)
+    layers = _layers(pkg, golden_compnet)
+    nonempty = [s for s in minu_sets if len(s[0])]
+    assert len(got.minu) == len(nonempty) and len(got.tex) == 1
+    for g, (xyo, des) in zip(got.minu, nonempty):
+        assert np.array_equal(g.x, xyo[:, 0].astype(np.int16)) and g.des.shape == (len(xyo), 96)
+        np.testing.assert_allclose(g.des, co.compress(layers, des), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got.tex[0].des, co.compress(layers, tex_sets[0][1]), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(got.tex[0].x, ((tex_sets[0][0][:, 0] - 24) / 16).astype(np.int16))

@@ -290,3 +290,25 @@ def test_enroll_rolled_writes_the_reference_layout(pkg, matcher, golden, tmp_pat
             _, _, fin = R.score_pair(lh, rh)
             assert fin == a["scores"][0, g]
         R.close()
+
+
+def test_enroll_latent_writes_the_reference_layout(pkg, matcher, golden, tmp_path):
+    """lafis_enroll_latent (Template2Bin_Byte_latent, descriptor_PQ.py:80-175): byte-identical to the Python writer,
+    and the enrolled file scores exactly like the same latent packed in memory."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(8200 + g, n_minu=60, n_tex=200) for g in range(3)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    lat = T.synth_latent(91, raws[1], n_minu=35, n_tex_pts=70)
+    minu_sets = [(np.stack([m.x.astype(np.float32) + 0.5, m.y.astype(np.float32) + 0.25, m.ori], axis=1), m.des)
+                 for m in lat.minu]
+    tex_sets = [(np.stack([t.x.astype(np.float32) * 16 + 24 + 5, t.y.astype(np.float32) * 16 + 24, t.ori], axis=1), t.des)
+                for t in lat.tex]
+    p, q = os.path.join(str(tmp_path), "lat_c.dat"), os.path.join(str(tmp_path), "lat_py.dat")
+    matcher.enroll_latent(p, minu_sets, tex_sets, h=lat.h, w=lat.w, blkH=lat.blkH, blkW=lat.blkW)
+    T.write_template(q, lat)
+    assert open(p, "rb").read() == open(q, "rb").read()
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    a = matcher.match(matcher.load_latents([p]), topk=3)
+    b = matcher.match(matcher.latents_from_packed(pkg.pack_latents([lat])), topk=3)
+    assert np.array_equal(a["scores"], b["scores"]) and a["hits"][0]["index"][0] == 1
