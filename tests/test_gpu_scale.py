@@ -66,3 +66,110 @@ def test_100k_gallery_properties(pkg, built, golden, oracle):
             assert st["tex_overflow"] == 0 and st["tex_exact"] < 0.02 * st["tex_templates"] * 16 * 800
     finally:
         m.close()
+
+
+def test_config5_shard_protocol(pkg, built, golden, tmp_path):
+    """SURVEY.md §8d "Parity protocol at scale" on one GPU's share of BASELINE.json configs[4] (a batch of latents vs a
+    gallery shard far beyond what the CPU reference can score in full): for a stated sample of latents the GPU's
+    top-1000 and a random sample of the remainder are re-scored by the reference matcher itself (oracle/_ref; the
+    plain-C oracle when it is absent) - scores bit-identical, top-100 order identical, no sampled non-candidate above
+    the 100th score; for ALL latents the rank list is the (score desc, index asc) order of the full score row and
+    the mate is first.  Default sizes keep the test short; LAFIS_SCALE_FULL=1 runs 256 latents x 125,000 prints
+    (configs[4] / 8 GPUs) with 10,000 sampled non-candidates, LAFIS_SCALE_REPORT=<path> writes the JSON report."""
+    import json
+    import os
+    import time
+    import torch
+    import refbind
+    from msu_latentafis_b200.synth import synth_gallery_device
+    full = os.environ.get("LAFIS_SCALE_FULL") == "1"
+    Q, Gs, n_rand, probe = (256, 125_000, 10_000, [0, 37, 101, 255]) if full else (48, 40_000, 1_500, [0, 31])
+    K, KTOP = 100, 1000
+    T = pkg.templates
+    cb = golden["codebook"]
+    m = pkg.Matcher(codebook=cb, device=0)
+    try:
+        with torch.cuda.stream(torch.cuda.ExternalStream(m.stream)):
+            raws = [T.synth_rolled_raw(g) for g in range(Q)]
+            codes = m.pq_encode(np.concatenate([r.tex_des for r in raws]))
+            head, at = [], 0
+            for r in raws:
+                k = r.tex_x.shape[0]
+                head.append(T.FPTemplate(h=T.IMG_H, w=T.IMG_W, blkH=50, blkW=48, minu=[r.minu],
+                                         tex=[T.TextureTemplate(r.tex_x, r.tex_y, r.tex_ori, codes[at:at + k])]))
+                at += k
+            latents = [T.synth_latent(q, raws[q]) for q in range(Q)]
+            m.set_gallery(synth_gallery_device(m, Gs, seed=4242, head=head))
+            L = m.latents_from_packed(pkg.pack_latents(latents))
+            t0 = time.perf_counter()
+            out = m.match(L, topk=KTOP)
+            gpu_s = time.perf_counter() - t0
+        scores, hits = out["scores"], out["hits"]
+        # every latent: mate first, rank list = (score desc, index asc) order of its full score row
+        for q in range(Q):
+            order = np.lexsort((np.arange(Gs), -scores[q].astype(np.float64)))[:KTOP]
+            assert np.array_equal(hits[q]["index"], order), q
+            assert np.array_equal(hits[q]["score"], scores[q][order]), q
+            assert hits[q]["index"][0] == q, q
+        # probe latents: the reference itself on the GPU's top-1000 and on a random sample of the rest
+        rng = np.random.default_rng(99)
+        rand = rng.choice(Gs, n_rand, replace=False)
+        cbp = os.path.join(str(tmp_path), "cb.dat")
+        T.write_codebook(cbp, cb)
+        use_ref = refbind.available()
+        R = refbind.RefMatcher(cbp) if use_ref else None
+        ob = None if use_ref else entry_oracle()
+        cache = {}
+
+        def handle(i):
+            if i not in cache:
+                tpl = m.gallery_template(int(i))
+                if use_ref:
+                    p = os.path.join(str(tmp_path), "g.dat")
+                    T.write_template(p, tpl)
+                    cache[i] = R.load_rolled(p)[0]
+                else:
+                    cache[i] = ob.OracleRolled(tpl)
+            return cache[i]
+
+        report = {"latents": Q, "gallery": Gs, "gpu_match_s": gpu_s, "probe_latents": probe, "top_rescored": KTOP,
+                  "random_rescored": int(n_rand), "checker": "oracle/_ref (reference matcher)" if use_ref else "oracle port",
+                  "pairs_rescored": 0, "max_rel_diff": 0.0, "bit_identical": True, "top100_identical": True,
+                  "sampled_noncandidates_above_100th": 0}
+        t0 = time.perf_counter()
+        for q in probe:
+            idx = np.unique(np.concatenate([hits[q]["index"].astype(np.int64), rand]))
+            hs = [handle(int(i)) for i in idx]
+            if use_ref:
+                lp = os.path.join(str(tmp_path), "l.dat")
+                T.write_template(lp, latents[q])
+                lh, _ = R.load_latent(lp)
+                _, want, _ = R.score_gallery(lh, hs, os.cpu_count() or 1)
+            else:
+                OL = ob.OracleLatent(latents[q], cb)
+                want = np.array([ob.score_pair(OL, h)[2] for h in hs], np.float32)
+            got = scores[q][idx]
+            report["pairs_rescored"] += int(len(idx))
+            report["max_rel_diff"] = max(report["max_rel_diff"],
+                                         float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-6))))
+            report["bit_identical"] &= bool(np.array_equal(got, want))
+            # top-100 of the re-scored set by the reference's scores == the GPU's top-100
+            ref_order = idx[np.lexsort((idx, -want.astype(np.float64)))][:K]
+            report["top100_identical"] &= bool(np.array_equal(ref_order, hits[q]["index"][:K].astype(np.int64)))
+            in_top = np.isin(idx, hits[q]["index"][:KTOP])
+            report["sampled_noncandidates_above_100th"] += int(np.sum(want[~in_top] > hits[q]["score"][K - 1]))
+        report["checker_s"] = time.perf_counter() - t0
+        if R is not None:
+            R.close()
+        if os.environ.get("LAFIS_SCALE_REPORT"):
+            with open(os.environ["LAFIS_SCALE_REPORT"], "w") as f:
+                json.dump(report, f, indent=1)
+        assert report["bit_identical"] and report["max_rel_diff"] == 0.0, report
+        assert report["top100_identical"] and report["sampled_noncandidates_above_100th"] == 0, report
+    finally:
+        m.close()
+
+
+def entry_oracle():
+    import __graft_entry__ as entry
+    return entry.load_oracle()
