@@ -133,6 +133,7 @@ struct lafis_ctx {
     DevBuf<unsigned long long> keys_a, keys_b;
     DevBuf<HitDev> hits;
     DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
+    DevBuf<float> compnet_h1;         // CompNet: output of layer1, [n][96]
     int* d_job_counter = nullptr;
     unsigned long long* d_slow = nullptr;  // [8] counters: 0 minutiae introsort replays, 1 texture top-200 replays,
                                            //     4..7 texture row-max: queued, exact evaluations, overflowed, templates
@@ -237,7 +238,8 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
                                  (int)sizeof(SparseWork<false>)));
         TRY(cudaFuncSetAttribute(graph_tex_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SparseWork<true>)));
-        TRY(cudaFuncSetAttribute(compnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compnet_smem_bytes()));
+        TRY(cudaFuncSetAttribute(compnet_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compnet_l1_smem_bytes()));
+        TRY(cudaFuncSetAttribute(compnet_l234_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compnet_l234_smem_bytes()));
     }
 #undef TRY
     if (!ok) {
@@ -308,6 +310,7 @@ void lafis_destroy(lafis_ctx* c) {
     c->keys_b.release();
     c->hits.release();
     c->lat_arena.release();
+    c->compnet_h1.release();
     cudaFree(c->d_codebook);
     cudaFree(c->d_table);
     cudaFree(c->d_compnet);
@@ -1433,6 +1436,7 @@ int lafis_compress_descriptors(lafis_ctx* c, const float* des_in, int64_t n, flo
     float* d_out = des_out;
     float* tmp_in = nullptr;
     float* tmp_out = nullptr;
+    LAFIS_CUDA(c, c->compnet_h1.reserve((size_t)n * kCompOut));
     if (!on_device) {
         LAFIS_CUDA(c, cudaMalloc(&tmp_in, sizeof(float) * kCompIn * (size_t)n));
         if (cudaMalloc(&tmp_out, sizeof(float) * kCompOut * (size_t)n) != cudaSuccess) {
@@ -1446,14 +1450,17 @@ int lafis_compress_descriptors(lafis_ctx* c, const float* des_in, int64_t n, flo
     CompNetParams P;
     P.x = d_in;
     P.n = (long long)n;
+    P.h1 = c->compnet_h1.p;
     P.out = d_out;
     P.wt = c->d_compnet;
     P.aff = c->d_compnet + kCompWeightFloats;
     P.normalise = normalise;
     const long long groups = (n + kCompPts - 1) / kCompPts;
-    const unsigned grid = (unsigned)std::min<long long>(c->sm_count, (groups + kCompWarps - 1) / kCompWarps);
-    compnet_kernel<<<grid, kCompWarps * 32, compnet_smem_bytes(), c->stream>>>(P);
-    c->stats.kernel_launches += 1;
+    const unsigned grid1 = (unsigned)std::min<long long>(c->sm_count, (groups + kCompWarpsL1 - 1) / kCompWarpsL1);
+    const unsigned grid2 = (unsigned)std::min<long long>(c->sm_count, (groups + kCompWarpsL234 - 1) / kCompWarpsL234);
+    compnet_l1_kernel<<<grid1, kCompWarpsL1 * 32, compnet_l1_smem_bytes(), c->stream>>>(P);
+    compnet_l234_kernel<<<grid2, kCompWarpsL234 * 32, compnet_l234_smem_bytes(), c->stream>>>(P);
+    c->stats.kernel_launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !on_device)
         e = cudaMemcpyAsync(des_out, tmp_out, sizeof(float) * kCompOut * (size_t)n, cudaMemcpyDeviceToHost, c->stream);

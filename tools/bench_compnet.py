@@ -1,4 +1,4 @@
-"""Dev helper: device-resident throughput of compnet_kernel (descriptors/s and fp32 FMA rate), CUDA events."""
+"""Dev helper: device-resident throughput of the two CompNet kernels (descriptors/s and fp32 FMA rate), CUDA events."""
 import os, sys
 import numpy as np
 import torch
@@ -25,6 +25,6 @@ e1.record(s)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 fma = n * 46080 / (ms * 1e-3)
-print(f"compnet_kernel: {n} descriptors in {ms:.3f} ms = {n / ms / 1e3:.1f} M descriptors/s, {fma / 1e12:.2f} T FMA/s "
+print(f"compnet_l1_kernel + compnet_l234_kernel: {n} descriptors in {ms:.3f} ms = {n / ms / 1e3:.1f} M descriptors/s, {fma / 1e12:.2f} T FMA/s "
       f"({fma / (148 * 128 * 1.965e9) * 100:.1f} % of the fp32 FMA issue rate), {n * (192 + 96) * 4 / ms / 1e6:.0f} GB/s HBM")
 m.close()
