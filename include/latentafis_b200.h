@@ -32,7 +32,8 @@ enum {
     LAFIS_ERR_IO = -3,
     LAFIS_ERR_CODEBOOK = -4,       /* not a 16 x 256 x 6 codebook */
     LAFIS_ERR_CUDA = -5,
-    LAFIS_ERR_UNSUPPORTED_SIZE = -6, /* template larger than the device kernels are built for */
+    LAFIS_ERR_UNSUPPORTED_SIZE = -6, /* more than 2000 points in a template: the reference's loaders reject it too
+                                        (matcher.cpp:837-841, :865-869) */
     LAFIS_ERR_LATENT_LAYOUT = -7,  /* score[28] would be read out of bounds by the reference
                                       (matcher.cpp:188): latent has < 29 template slots */
     LAFIS_ERR_NO_GALLERY = -8
@@ -278,6 +279,8 @@ typedef struct {
     uint64_t tex_exact;       /* ... of which re-evaluated exactly in fp32 */
     uint64_t tex_overflow;    /* ... (warp, template) visits whose queue overflowed: evaluated exactly in full */
     uint64_t tex_templates;   /* ... (warp, template) visits in total */
+    uint64_t minu_big_jobs;   /* (latent, template, minutiae slot) jobs too large for the shared-memory tiles, scored
+                                 by the HBM-resident kernels (same results, slower) */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 /* 2 (default): the texture chain runs on a second CUDA stream concurrently with the minutiae chain;

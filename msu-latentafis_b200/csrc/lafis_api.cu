@@ -21,6 +21,7 @@
 #include "device_common.cuh"
 #include "graph_prune.cuh"
 #include "graph_sparse.cuh"
+#include "minu_big.cuh"
 #include "minu_sim.cuh"
 #include "misc_kernels.cuh"
 #include "tex_rowmax.cuh"
@@ -134,6 +135,11 @@ struct lafis_ctx {
     DevBuf<HitDev> hits;
     DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
     DevBuf<float> compnet_h1;         // CompNet: output of layer1, [n][96]
+    // oversized minutiae pairs (minu_big.cuh): work list and matrices in HBM
+    DevBuf<int> big_jobs, big_slow;
+    DevBuf<unsigned long long> big_soff;
+    DevBuf<float> big_S;
+    DevBuf<uint32_t> big_keys, big_order;
     int* d_job_counter = nullptr;
     unsigned long long* d_slow = nullptr;  // [8] counters: 0 minutiae introsort replays, 1 texture top-200 replays,
                                            //     4..7 texture row-max: queued, exact evaluations, overflowed, templates
@@ -252,6 +258,63 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     return LAFIS_OK;
 }
 
+// Shared-memory geometry of the fast minutiae kernels (minu_sim.cuh) for a latent batch and a gallery.  They take
+// latent slots of <= l_cap and gallery templates of <= r_cap minutiae; everything larger goes to minu_big.cuh.
+struct MinuPlan {
+    int l_cap = 1, r_cap = 4;
+    int maxL = 1, maxNp = 4;
+    int a_slot_stride = 0, b_buf_stride = 0, b_double = 1;
+    size_t sim_smem = 0, sel_smem = 0, slow_smem = 0, job_stride = 0;
+    bool slow_dense = false;
+    bool efficient = false;  // double-buffered similarity kernel and four selection CTAs per SM
+};
+constexpr int kFastMaxL = 128;  // three resident latent blocks of 128 minutiae are 148 KB of shared memory
+
+bool minu_plan_fill(MinuPlan& p, int L, int Np) {
+    p.maxL = L;
+    p.maxNp = Np;
+    const int maxLp = (L + 3) & ~3;
+    p.a_slot_stride = 96 * maxLp + 16;
+    p.b_buf_stride = 96 * Np + 160;
+    p.b_double = minu_sim_smem_bytes(p.a_slot_stride, p.b_buf_stride, 1) <= (size_t)kMaxDynSmem ? 1 : 0;
+    p.sim_smem = minu_sim_smem_bytes(p.a_slot_stride, p.b_buf_stride, p.b_double);
+    p.sel_smem = minu_select_smem_bytes(L, Np);
+    // the dense key copy enables the block-parallel introsort replay; one CTA per SM is enough for this rare path
+    p.slow_dense = minu_select_slow_smem_bytes(L, Np, true) <= (size_t)kMaxDynSmem;
+    p.slow_smem = minu_select_slow_smem_bytes(L, Np, p.slow_dense);
+    p.job_stride = (size_t)L * Np;
+    p.efficient = p.b_double && 4 * (p.sel_smem + 2048) <= (size_t)228 * 1024;
+    p.l_cap = L;
+    p.r_cap = Np;
+    return p.sim_smem <= (size_t)kMaxDynSmem && p.slow_smem <= (size_t)kMaxDynSmem && p.sel_smem <= (size_t)kMaxDynSmem &&
+           (size_t)L * Np < 65536;
+}
+
+// max_nR: largest template among the n templates whose minutiae counts are in h_n (may be NULL)
+MinuPlan plan_minu(int max_slot_n, int max_nR, const uint16_t* h_n, size_t n) {
+    MinuPlan p;
+    const int L = std::min(std::max(1, max_slot_n), kFastMaxL);
+    int Np = std::max(4, (max_nR + 3) & ~3);
+    while (Np > 4 && !minu_plan_fill(p, L, Np)) Np -= 4;
+    minu_plan_fill(p, L, Np);
+    if (!p.efficient && h_n && n > 0) {
+        // one outsized template must not push the whole gallery onto the slow geometry: when at most 0.5 % of the
+        // templates exceed the largest efficient tile, they are the ones that go to the big-pair kernels
+        MinuPlan e;
+        int Ne = Np;
+        while (Ne > 4) {
+            if (minu_plan_fill(e, L, Ne) && e.efficient) break;
+            Ne -= 4;
+        }
+        if (Ne > 4 && Ne < Np) {
+            size_t big = 0;
+            for (size_t i = 0; i < n; ++i) big += h_n[i] > Ne;
+            if (big * 200 <= n) p = e;
+        }
+    }
+    return p;
+}
+
 // Everything a packed gallery needs on the host before the device re-layout.
 struct IngestPlan {
     std::vector<uint32_t> dst_minu_off, dst_tex_off;
@@ -311,6 +374,12 @@ void lafis_destroy(lafis_ctx* c) {
     c->hits.release();
     c->lat_arena.release();
     c->compnet_h1.release();
+    c->big_jobs.release();
+    c->big_slow.release();
+    c->big_soff.release();
+    c->big_S.release();
+    c->big_keys.release();
+    c->big_order.release();
     cudaFree(c->d_codebook);
     cudaFree(c->d_table);
     cudaFree(c->d_compnet);
@@ -850,6 +919,54 @@ int lafis_latents_make_resident(lafis_ctx* c, lafis_latents* l) {
 // ---------------------------------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------------------------------
+// Oversized minutiae pairs: the work list `jobs` (sizes[k] = nL * padded nR elements of job k) in sub-batches whose
+// matrices fit a bounded scratch area; results land in the fast path's corr_* arrays before the graph stage reads them.
+static int run_big_jobs(lafis_ctx* c, cudaStream_t st, MinuBigParams B, const std::vector<int>& jobs,
+                        const std::vector<unsigned long long>& sizes) {
+    constexpr unsigned long long kBatchElems = 48ull << 20;  // 192 MB per scratch array
+    const size_t n = jobs.size();
+    c->stats.minu_big_jobs += n;
+    size_t at = 0;
+    while (at < n) {
+        std::vector<unsigned long long> off;
+        unsigned long long tot = 0;
+        size_t end = at;
+        while (end < n && (end == at || tot + sizes[end] <= kBatchElems)) {
+            off.push_back(tot);
+            tot += (sizes[end] + 3ull) & ~3ull;  // keep every matrix 16-byte aligned
+            ++end;
+        }
+        const int nb = (int)(end - at);
+        LAFIS_CUDA(c, c->big_jobs.reserve(nb));
+        LAFIS_CUDA(c, c->big_slow.reserve(nb));
+        LAFIS_CUDA(c, c->big_soff.reserve(nb));
+        LAFIS_CUDA(c, c->big_S.reserve(tot));
+        LAFIS_CUDA(c, c->big_keys.reserve(tot));
+        LAFIS_CUDA(c, c->big_order.reserve(tot));
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->big_jobs.p, jobs.data() + at, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->big_soff.p, off.data(), sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
+        LAFIS_CUDA(c, cudaStreamSynchronize(st));  // `off` is a pageable temporary
+        LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
+        B.jobs = c->big_jobs.p;
+        B.s_off = c->big_soff.p;
+        B.n_jobs = nb;
+        B.S = c->big_S.p;
+        B.keys = c->big_keys.p;
+        B.order = c->big_order.p;
+        B.slow_count = c->d_slow_count;
+        B.slow_list = c->big_slow.p;
+        B.replay_count = c->d_slow;
+        const size_t smem = minu_big_select_smem_bytes(B.max_nL, B.max_np);
+        minu_big_sim_kernel<<<nb, 256, 0, st>>>(B);
+        minu_big_select_kernel<<<nb, kSelThreads, smem, st>>>(B);
+        minu_big_slow_kernel<<<std::min(nb, 2 * c->sm_count), kSelThreads, smem, st>>>(B);
+        c->stats.kernel_launches += 3;
+        LAFIS_CUDA(c, cudaGetLastError());
+        at = end;
+    }
+    return LAFIS_OK;
+}
+
 static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     const int Q = L->n, G = c->gal.n;
     if (G <= 0) return fail(c, LAFIS_ERR_NO_GALLERY, "no gallery resident");
@@ -884,21 +1001,14 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     D.status = reinterpret_cast<int*>(A + L->o_status);
 
     // ---- geometry ----
-    const int maxL = std::max(1, L->max_slot_n), maxLp = (maxL + 3) & ~3;
-    const int maxNp = std::max(4, (c->max_nR + 3) & ~3);
-    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 160;
-    int b_double = 1;
-    if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
-    const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
-    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp);
-    // the dense key copy enables the block-parallel introsort replay; one CTA per SM is enough for this rare path
-    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem;
-    const size_t slow_smem = minu_select_slow_smem_bytes(maxL, maxNp, slow_dense);
-    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || sel_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
-        return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE,
-                    "minutiae templates of %d x %d points need %zu / %zu bytes of shared memory (limit %d)",
-                    L->max_slot_n, c->max_nR, sim_smem, slow_smem, kMaxDynSmem);
-    const size_t job_stride = (size_t)maxL * maxNp;
+    const MinuPlan plan = plan_minu(L->max_slot_n, c->max_nR, c->h_minu_n.data(), c->h_minu_n.size());
+    const int maxL = plan.maxL, maxNp = plan.maxNp;
+    const int a_slot_stride = plan.a_slot_stride, b_buf_stride = plan.b_buf_stride, b_double = plan.b_double;
+    const size_t sim_smem = plan.sim_smem, sel_smem = plan.sel_smem, slow_smem = plan.slow_smem;
+    const bool slow_dense = plan.slow_dense;
+    const size_t job_stride = plan.job_stride;
+    // pairs beyond the fast kernels' tiles (minu_big.cuh)
+    const bool has_big = L->max_slot_n > plan.l_cap || c->max_nR > plan.r_cap;
     const size_t lt = (size_t)L->lt_stride;
     const size_t per_tpl = (size_t)Q * (lt * 6 + 3 * (kTopCorrMinu * 8 + 4) + 3 * job_stride * 4 + 32);
     size_t chunk_sz = std::max<size_t>(1, c->work_budget / std::max<size_t>(per_tpl, 1));
@@ -973,6 +1083,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.b_double = b_double;
             P.S = c->sim.p;
             P.job_stride = job_stride;
+            P.l_cap = plan.l_cap;
+            P.r_cap = plan.r_cap;
             {
                 int g = c->sm_count, r = Q;  // gcd(Q, SMs)
                 while (r) {
@@ -999,6 +1111,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             R.job_stride = job_stride;
             R.max_nL = maxL;
             R.max_np = maxNp;
+            R.l_cap = plan.l_cap;
+            R.r_cap = plan.r_cap;
             R.slow_dense = slow_dense ? 1 : 0;
             R.corr_v = c->corr_v.p;
             R.corr_ij = c->corr_ij.p;
@@ -1011,6 +1125,50 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             end(2, st);
             begin(6, st);
             minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
+            if (has_big) {
+                // work list of this chunk: every (latent, slot) against the oversized templates, and oversized
+                // latent slots against every template
+                std::vector<int> big_tl;
+                for (int tl = 0; tl < n_chunk; ++tl)
+                    if (c->h_minu_n[g0 + tl] > plan.r_cap) big_tl.push_back(tl);
+                std::vector<int> bj;
+                std::vector<unsigned long long> bsz;
+                for (int q = 0; q < Q; ++q) {
+                    if (L->status[q] != LAFIS_OK) continue;
+                    for (int slot = 0; slot < 3; ++slot) {
+                        const int nLs = L->slot_n[q * 3 + slot];
+                        if (nLs <= 0) continue;
+                        auto push = [&](int tl) {
+                            const int nR = c->h_minu_n[g0 + tl];
+                            if (nR <= 0) return;
+                            bj.push_back((int)(((size_t)q * n_chunk + tl) * 3 + slot));
+                            bsz.push_back((unsigned long long)nLs * ((nR + 3) & ~3));
+                        };
+                        if (nLs > plan.l_cap) {
+                            for (int tl = 0; tl < n_chunk; ++tl) push(tl);
+                        } else {
+                            for (int tl : big_tl) push(tl);
+                        }
+                    }
+                }
+                MinuBigParams B;
+                B.slot_n = D.slot_n;
+                B.slot_off = D.slot_off;
+                B.lat_desT = D.minu_desT;
+                B.lat_status = D.status;
+                B.minu_off = c->gal.minu_off;
+                B.minu_n = c->gal.minu_n;
+                B.minu_desT = c->gal.minu_desT;
+                B.g0 = g0;
+                B.n_chunk = n_chunk;
+                B.max_nL = std::max(1, L->max_slot_n);
+                B.max_np = std::max(4, (c->max_nR + 3) & ~3);
+                B.corr_v = c->corr_v.p;
+                B.corr_ij = c->corr_ij.p;
+                B.corr_n = c->corr_n.p;
+                const int rc_big = run_big_jobs(c, st, B, bj, bsz);
+                if (rc_big != LAFIS_OK) return rc_big;
+            }
         }
         end(6, st);
         // ---- texture chain (stream sb): K2 + K3a, then K3b + K4 + K9 ----
@@ -1179,18 +1337,13 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
         A = c->lat_arena.p;
         LAFIS_CUDA(c, cudaMemcpyAsync(A, L->pinned, L->arena_bytes, cudaMemcpyHostToDevice, st));
     }
-    const int maxL = std::max(1, L->max_slot_n), maxLp = (maxL + 3) & ~3;
-    const int maxNp = std::max(4, (c->max_nR + 3) & ~3);
-    const int a_slot_stride = 96 * maxLp + 16, b_buf_stride = 96 * maxNp + 160;
-    int b_double = 1;
-    if (minu_sim_smem_bytes(a_slot_stride, b_buf_stride, 1) > (size_t)kMaxDynSmem) b_double = 0;
-    const size_t sim_smem = minu_sim_smem_bytes(a_slot_stride, b_buf_stride, b_double);
-    const size_t sel_smem = minu_select_smem_bytes(maxL, maxNp);
-    const bool slow_dense = minu_select_slow_smem_bytes(maxL, maxNp, true) <= (size_t)kMaxDynSmem;
-    const size_t slow_smem = minu_select_slow_smem_bytes(maxL, maxNp, slow_dense);
-    if (sim_smem > (size_t)kMaxDynSmem || slow_smem > (size_t)kMaxDynSmem || sel_smem > (size_t)kMaxDynSmem || (size_t)maxL * maxNp >= 65536)
-        return fail(c, LAFIS_ERR_UNSUPPORTED_SIZE, "minutiae templates of %d x %d points exceed the shared-memory tiles", L->max_slot_n, c->max_nR);
-    const size_t job_stride = (size_t)maxL * maxNp;
+    const int nR_gi = c->h_minu_n[gi];
+    const MinuPlan plan = plan_minu(L->max_slot_n, nR_gi, nullptr, 0);
+    const int maxL = plan.maxL, maxNp = plan.maxNp;
+    const int a_slot_stride = plan.a_slot_stride, b_buf_stride = plan.b_buf_stride, b_double = plan.b_double;
+    const size_t sim_smem = plan.sim_smem, sel_smem = plan.sel_smem, slow_smem = plan.slow_smem;
+    const bool slow_dense = plan.slow_dense;
+    const size_t job_stride = plan.job_stride;
     const unsigned jobs = (unsigned)Q * 3u;
     LAFIS_CUDA(c, c->corr_v.reserve((size_t)jobs * kTopCorrMinu));
     LAFIS_CUDA(c, c->corr_ij.reserve((size_t)jobs * kTopCorrMinu));
@@ -1219,6 +1372,8 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     P.S = c->sim.p;
     P.job_stride = job_stride;
     P.parts = 1;
+    P.l_cap = plan.l_cap;
+    P.r_cap = plan.r_cap;
     minu_sim_kernel<<<1, kSimThreads, sim_smem, st>>>(P);
     MinuSelectParams R;
     R.slot_n = P.slot_n;
@@ -1231,6 +1386,8 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     R.job_stride = job_stride;
     R.max_nL = maxL;
     R.max_np = maxNp;
+    R.l_cap = plan.l_cap;
+    R.r_cap = plan.r_cap;
     R.slow_dense = slow_dense ? 1 : 0;
     R.corr_v = c->corr_v.p;
     R.corr_ij = c->corr_ij.p;
@@ -1240,6 +1397,33 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
     minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
     minu_select_slow_kernel<<<std::min<unsigned>(jobs, (unsigned)c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
+    if (nR_gi > 0 && L->status[q] == LAFIS_OK && (nR_gi > plan.r_cap || L->max_slot_n > plan.l_cap)) {
+        std::vector<int> bj;
+        std::vector<unsigned long long> bsz;
+        for (int slot = 0; slot < 3; ++slot) {
+            const int nLs = L->slot_n[q * 3 + slot];
+            if (nLs <= 0 || (nLs <= plan.l_cap && nR_gi <= plan.r_cap)) continue;
+            bj.push_back(q * 3 + slot);
+            bsz.push_back((unsigned long long)nLs * ((nR_gi + 3) & ~3));
+        }
+        MinuBigParams B;
+        B.slot_n = P.slot_n;
+        B.slot_off = P.slot_off;
+        B.lat_desT = P.lat_desT;
+        B.lat_status = P.lat_status;
+        B.minu_off = c->gal.minu_off;
+        B.minu_n = c->gal.minu_n;
+        B.minu_desT = c->gal.minu_desT;
+        B.g0 = gi;
+        B.n_chunk = 1;
+        B.max_nL = std::max(1, L->max_slot_n);
+        B.max_np = std::max(4, (nR_gi + 3) & ~3);
+        B.corr_v = c->corr_v.p;
+        B.corr_ij = c->corr_ij.p;
+        B.corr_n = c->corr_n.p;
+        const int rc_big = run_big_jobs(c, st, B, bj, bsz);
+        if (rc_big != LAFIS_OK) return rc_big;
+    }
     // every job of latent q goes through the dense graph kernel, which can list its survivors
     const int h_jobs[3] = {q * 3 + 0, q * 3 + 1, q * 3 + 2};
     const int h_count = 3;

@@ -64,6 +64,7 @@ struct MinuSimParams {
     int b_buf_stride;   // one gallery block: 96 * max padded template count + 160
     int b_double;       // two gallery buffers
     int parts;          // jobs per latent (see minu_sim_kernel)
+    int l_cap, r_cap;   // latent slots / gallery templates with more minutiae are skipped here (minu_big.cuh takes them)
     // output: S[job][i * np + j], job = (q * n_chunk + tl) * 3 + slot
     float* S;
     size_t job_stride;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
     auto load_B = [&](int tl, int buf) {
         const int g = P.g0 + tl;
         const int nR = P.minu_n[g];
-        if (nR <= 0) return;
+        if (nR <= 0 || nR > P.r_cap) return;
         const int np = (nR + 3) & ~3;
         const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * P.minu_off[g]);
         float4* dst = reinterpret_cast<float4*>(B + (size_t)buf * P.b_buf_stride);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
     auto load_A = [&](int q) {
         for (int s = 0; s < 3; ++s) {
             const int nL = P.slot_n[q * 3 + s];
-            if (nL <= 0) continue;
+            if (nL <= 0 || nL > P.l_cap) continue;
             const int np = (nL + 3) & ~3;
             const float4* src = reinterpret_cast<const float4*>(P.lat_desT + (size_t)96 * P.slot_off[q * 3 + s]);
             float4* dst = reinterpret_cast<float4*>(A + (size_t)s * P.a_slot_stride);
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
         const int tiles_j = (nR + 127) >> 7;
 
         for (int q = 0; q < P.Q; ++q) {
-            const bool live = P.lat_status[q] == 0 && nR > 0;
+            const bool live = P.lat_status[q] == 0 && nR > 0 && nR <= P.r_cap;
             if (P.Q > 1) {
                 __syncthreads();  // previous latent's tiles are done with A
                 if (live) load_A(q);
@@ -214,7 +215,10 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
             int t0[4];
             t0[0] = 0;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_jj;
+            for (int s = 0; s < 3; ++s) {
+                const int rows = P.slot_n[q * 3 + s] <= P.l_cap ? P.slot_n[q * 3 + s] : 0;
+                t0[s + 1] = t0[s] + ((rows + 15) >> 4) * tiles_jj;
+            }
             for (int t = warp; t < t0[3]; t += NW) {
                 const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
                 const int tt = t - t0[s];
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
     auto load_B = [&](int tl, int buf) {
         const int g = P.g0 + tl;
         const int nR = P.minu_n[g];
-        if (nR <= 0) return;
+        if (nR <= 0 || nR > P.r_cap) return;
         const int np = (nR + 3) & ~3;
         const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * P.minu_off[g]);
         float4* dst = reinterpret_cast<float4*>(B + (size_t)buf * P.b_buf_stride);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
     auto load_A = [&](int q) {
         for (int s = 0; s < 3; ++s) {
             const int nL = P.slot_n[q * 3 + s];
-            if (nL <= 0) continue;
+            if (nL <= 0 || nL > P.l_cap) continue;
             const int np = (nL + 3) & ~3;
             const float4* src = reinterpret_cast<const float4*>(P.lat_desT + (size_t)96 * P.slot_off[q * 3 + s]);
             float4* dst = reinterpret_cast<float4*>(A + (size_t)s * P.a_slot_stride);
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
             if (prefetched) cp_async_wait<1>();
             else cp_async_wait<0>();
             __syncthreads();
-            if (nR > 0) {
+            if (nR > 0 && nR <= P.r_cap) {
                 // tile list over the three slots.  A warp tile is 16 rows x 16*NC columns (8 x NC per thread);
                 // templates of up to 160 minutiae are spanned by ONE tile of the smallest sufficient width, larger
                 // ones by 128-column tiles.
@@ -314,7 +318,10 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
                 int t0[4];
                 t0[0] = 0;
 #pragma unroll
-                for (int s = 0; s < 3; ++s) t0[s + 1] = t0[s] + ((P.slot_n[q * 3 + s] + 15) >> 4) * tiles_jj;
+                for (int s = 0; s < 3; ++s) {
+                    const int rows = P.slot_n[q * 3 + s] <= P.l_cap ? P.slot_n[q * 3 + s] : 0;
+                    t0[s + 1] = t0[s] + ((rows + 15) >> 4) * tiles_jj;
+                }
                 for (int t = warp; t < t0[3]; t += NW) {
                     const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
                     const int tt = t - t0[s];
@@ -353,6 +360,7 @@ struct MinuSelectParams {
     const float* S;
     size_t job_stride;
     int max_nL, max_np;  // shared-memory geometry
+    int l_cap, r_cap;    // larger latent slots / gallery templates are left to minu_big.cuh (corr_n = 0 here)
     int slow_dense;      // minu_select_slow_kernel keeps a dense copy of the keys
     float* corr_v;       // [job][120]
     uint32_t* corr_ij;   // [job][120] (i << 16) | j
@@ -393,7 +401,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
     const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
     const int nR = P.minu_n[P.g0 + tl];
     const int nL = (P.lat_status[q] == 0) ? P.slot_n[q * 3 + slot] : 0;
-    if (nL <= 0 || nR <= 0) {  // rolled without minutiae / latent slot absent: score stays 0
+    if (nL <= 0 || nR <= 0 || nL > P.l_cap || nR > P.r_cap) {
+        // rolled without minutiae / latent slot absent: score stays 0; oversized pairs are filled in by minu_big.cuh
         if (tid == 0) P.corr_n[job] = 0;
         return;
     }

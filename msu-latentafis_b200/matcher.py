@@ -84,7 +84,7 @@ class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_scored", C.c_uint64), ("last_match_ms", C.c_float),
                 ("last_stage_ms", C.c_float * 8), ("minu_replays", C.c_uint64), ("tex_replays", C.c_uint64),
                 ("tex_queued", C.c_uint64), ("tex_exact", C.c_uint64), ("tex_overflow", C.c_uint64),
-                ("tex_templates", C.c_uint64)]
+                ("tex_templates", C.c_uint64), ("minu_big_jobs", C.c_uint64)]
 
 
 _lib = None
@@ -545,7 +545,8 @@ class Matcher:
         return {"kernel_launches": int(s.kernel_launches), "pairs_scored": int(s.pairs_scored),
                 "last_match_ms": float(s.last_match_ms), "last_stage_ms": [float(x) for x in s.last_stage_ms],
                 "minu_replays": int(s.minu_replays), "tex_replays": int(s.tex_replays), "tex_queued": int(s.tex_queued),
-                "tex_exact": int(s.tex_exact), "tex_overflow": int(s.tex_overflow), "tex_templates": int(s.tex_templates)}
+                "tex_exact": int(s.tex_exact), "tex_overflow": int(s.tex_overflow), "tex_templates": int(s.tex_templates),
+                "minu_big_jobs": int(s.minu_big_jobs)}
 
     def set_streams(self, n: int) -> None:
         """2: texture chain on a second stream (default); 1: all kernels serialised on one stream."""

@@ -138,3 +138,37 @@ def test_large_images_take_the_dense_graph_kernel(pkg, built, golden, oracle):
     assert max(int(r.minu[0].x.max()) for r in rolled) > 2048
     st = _run(pkg, cb, latents, rolled, oracle)
     assert st["kernel_launches"] > 0
+
+
+def test_oversized_minutiae_templates(pkg, built, golden, oracle):
+    """Templates beyond the shared-memory tiles of the fast minutiae kernels - up to the reference's own limit of 2000
+    minutiae (matcher.cpp:788-841) - run through the HBM-resident kernels of minu_big.cuh: same candidate lists, same
+    scores.  Includes a latent whose slots exceed 128 minutiae (every pair of it is oversized), exact ties (duplicate
+    descriptors) and a template whose similarities are almost all zero (fewer than 120 positive values: the order is
+    the introsort's, replayed over ~50,000 equal keys)."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    sizes = [(120, 300), (300, 200), (450, 150), (700, 120), (2000, 64), (600, 100), (130, 400)]
+    raws = [T.synth_rolled_raw(3300 + k, n_minu=nm, n_tex=nt) for k, (nm, nt) in enumerate(sizes)]
+    raws[2].minu.des[1::2] = raws[2].minu.des[0::2]   # ties among the normalised similarities
+    raws[5].minu.des[1:] = 0.0                         # 599 all-zero columns of S
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(85, raws[1], n_minu=80, n_tex_pts=60),
+               T.synth_latent(86, raws[3], n_minu=150, n_tex_pts=40),   # slots of 150 > 128: oversized against everything
+               T.synth_latent(87, raws[4], n_minu=37, n_tex_pts=30)]
+    st = _run(pkg, cb, latents, rolled, oracle)
+    assert st["minu_big_jobs"] >= 3 * 7 + 2 * 3 * 4   # latent 1 x all templates, latents 0 and 2 x the templates beyond the tiles
+    assert st["minu_replays"] > 0
+
+
+def test_one_outsized_template_does_not_change_the_geometry(pkg, built, golden, oracle):
+    """A gallery of ordinary templates plus ONE of 420 minutiae: the fast kernels keep their efficient tiles (at most
+    0.5 % of the templates may exceed them) and the outlier alone goes through the oversized path."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(3400 + k, n_minu=100 + (k * 7) % 50, n_tex=80 + k % 40) for k in range(220)]
+    raws.insert(57, T.synth_rolled_raw(3999, n_minu=420, n_tex=90))
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(88, raws[57], n_minu=80, n_tex_pts=50)]
+    st = _run(pkg, cb, latents, rolled, oracle)
+    assert st["minu_big_jobs"] == 3
