@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -566,7 +567,7 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
     const int m = (int)(hi - lo);
     // Parse with all host cores: every thread reads a contiguous range of files into its own packed part
     // (the reference re-parses every rolled file for every latent, matcher.cpp:173/:278; here it happens once),
-    // then the parts are copied to their place in the final arrays, again in parallel.
+    // then every thread uploads its part to its place in the device staging arrays.
     struct Part {
         std::vector<uint32_t> n_minu, n_tex;  // per template
         std::vector<int16_t> mx, my, tx, ty;
@@ -603,7 +604,15 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
         fn(0);
         for (std::thread& th : pool) th.join();
     };
+    const bool timing = getenv("LAFIS_INGEST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(now() - t).count();
+    };
+    const auto t_parse = now();
     run_parallel(parse);
+    const double parse_ms = ms_since(t_parse);
+    const auto t_up = now();
     std::vector<uint32_t> minu_off(m + 1, 0), tex_off(m + 1, 0);
     std::vector<size_t> part_m(n_threads + 1, 0), part_t(n_threads + 1, 0);
     for (int i = 0; i < n_threads; ++i) {
@@ -617,39 +626,74 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
     }
     const size_t tot_m = part_m[n_threads], tot_t = part_t[n_threads];
     if (tot_m > 0xffffffffull / 2 || tot_t > 0xffffffffull / 2) return fail(c, LAFIS_ERR_ARG, "gallery shard too large for 32-bit offsets");
-    std::vector<int16_t> mx(tot_m), my(tot_m), tx(tot_t), ty(tot_t);
-    std::vector<float> mori(tot_m), mdes(tot_m * kDesLen), tori(tot_t);
-    std::vector<uint8_t> codes(tot_t * 16);
+    // Every parser thread uploads its own part straight to its place in device staging arrays (its own stream, so the
+    // pageable copies of different threads overlap); no consolidated host copy of the gallery is ever built.
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    void* dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t bytes[8] = {2 * tot_m, 2 * tot_m, 4 * tot_m, 4 * tot_m * kDesLen, 2 * tot_t, 2 * tot_t, 4 * tot_t, 16 * tot_t};
+    auto free_dev = [&]() {
+        for (void*& d : dev) {
+            if (d) cudaFree(d);
+            d = nullptr;
+        }
+    };
+    for (int k = 0; k < 8; ++k) {
+        const cudaError_t e = cudaMalloc(&dev[k], std::max<size_t>(bytes[k], 16));
+        if (e != cudaSuccess) {
+            free_dev();
+            return fail(c, LAFIS_ERR_CUDA, "gallery staging: cudaMalloc failed: %s", cudaGetErrorString(e));
+        }
+    }
+    std::vector<int> up_err(n_threads, 0);
     run_parallel([&](int i) {
         const Part& P = parts[i];
-        auto cp = [](void* d, const void* s_, size_t b) {
-            if (b) std::memcpy(d, s_, b);
+        cudaStream_t s_ = nullptr;
+        bool ok = cudaSetDevice(c->device) == cudaSuccess && cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking) == cudaSuccess;
+        auto cp = [&](int k, size_t elem_off, size_t elem_bytes, const void* src, size_t n_bytes) {
+            if (ok && n_bytes)
+                ok = cudaMemcpyAsync((char*)dev[k] + elem_off * elem_bytes, src, n_bytes, cudaMemcpyHostToDevice, s_) == cudaSuccess;
         };
-        cp(mx.data() + part_m[i], P.mx.data(), 2 * P.mx.size());
-        cp(my.data() + part_m[i], P.my.data(), 2 * P.my.size());
-        cp(mori.data() + part_m[i], P.mori.data(), 4 * P.mori.size());
-        cp(mdes.data() + part_m[i] * kDesLen, P.mdes.data(), 4 * P.mdes.size());
-        cp(tx.data() + part_t[i], P.tx.data(), 2 * P.tx.size());
-        cp(ty.data() + part_t[i], P.ty.data(), 2 * P.ty.size());
-        cp(tori.data() + part_t[i], P.tori.data(), 4 * P.tori.size());
-        cp(codes.data() + part_t[i] * 16, P.codes.data(), P.codes.size());
-        parts[i] = Part();  // release the part as soon as it has been copied
+        cp(0, part_m[i], 2, P.mx.data(), 2 * P.mx.size());
+        cp(1, part_m[i], 2, P.my.data(), 2 * P.my.size());
+        cp(2, part_m[i], 4, P.mori.data(), 4 * P.mori.size());
+        cp(3, part_m[i], 4 * kDesLen, P.mdes.data(), 4 * P.mdes.size());
+        cp(4, part_t[i], 2, P.tx.data(), 2 * P.tx.size());
+        cp(5, part_t[i], 2, P.ty.data(), 2 * P.ty.size());
+        cp(6, part_t[i], 4, P.tori.data(), 4 * P.tori.size());
+        cp(7, part_t[i], 16, P.codes.data(), P.codes.size());
+        if (s_) {
+            ok = cudaStreamSynchronize(s_) == cudaSuccess && ok;
+            cudaStreamDestroy(s_);
+        }
+        up_err[i] = ok ? 0 : 1;
+        parts[i] = Part();  // release the part as soon as it has been uploaded
     });
+    for (int e : up_err)
+        if (e) {
+            free_dev();
+            return fail(c, LAFIS_ERR_CUDA, "gallery staging: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     lafis_packed_gallery g{};
     g.n_templates = m;
     g.minu_off = minu_off.data();
-    g.minu_x = mx.data();
-    g.minu_y = my.data();
-    g.minu_ori = mori.data();
-    g.minu_des = mdes.data();
+    g.minu_x = static_cast<const int16_t*>(dev[0]);
+    g.minu_y = static_cast<const int16_t*>(dev[1]);
+    g.minu_ori = static_cast<const float*>(dev[2]);
+    g.minu_des = static_cast<const float*>(dev[3]);
     g.tex_off = tex_off.data();
-    g.tex_x = tx.data();
-    g.tex_y = ty.data();
-    g.tex_ori = tori.data();
-    g.tex_codes = codes.data();
+    g.tex_x = static_cast<const int16_t*>(dev[4]);
+    g.tex_y = static_cast<const int16_t*>(dev[5]);
+    g.tex_ori = static_cast<const float*>(dev[6]);
+    g.tex_codes = static_cast<const uint8_t*>(dev[7]);
     g.status = status.data();
-    g.on_device = 0;
+    g.on_device = 1;
+    const double up_ms = ms_since(t_up);
+    const auto t_set = now();
     int rc = lafis_gallery_set_packed(c, &g, (uint32_t)lo);
+    if (timing)
+        fprintf(stderr, "lafis ingest: %d files, %d threads: parse %.1f ms, upload %.1f ms, re-layout %.1f ms\n", m, n_threads,
+                parse_ms, up_ms, ms_since(t_set));
+    free_dev();
     if (rc == LAFIS_OK) c->paths.swap(kept);
     return rc;
 }
