@@ -172,3 +172,44 @@ def test_one_outsized_template_does_not_change_the_geometry(pkg, built, golden, 
     latents = [T.synth_latent(88, raws[57], n_minu=80, n_tex_pts=50)]
     st = _run(pkg, cb, latents, rolled, oracle)
     assert st["minu_big_jobs"] == 3
+
+
+def test_correspondences_of_an_oversized_pair(pkg, built, golden, tmp_path):
+    """lafis_correspondences (save_corr, matcher.cpp:497-505) when the pair goes through minu_big.cuh: the lists the
+    reference itself writes, and their similarities add up to the component scores."""
+    import os
+    import refbind
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(3500, n_minu=640, n_tex=100), T.synth_rolled_raw(3501, n_minu=110, n_tex=100)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(89, raws[0], n_minu=140, n_tex_pts=40)]
+    m = pkg.Matcher(codebook=cb, device=0)
+    try:
+        m.set_gallery(pkg.pack_rolled(rolled))
+        L = m.latents_from_packed(pkg.pack_latents(latents))
+        out = m.match(L, topk=2, want_components=True)
+        assert out["hits"][0]["index"][0] == 0 and m.stats()["minu_big_jobs"] == 6
+        got = [m.correspondences(L, 0, g) for g in range(2)]
+        for g in range(2):
+            assert all(len(c) <= 120 for c in got[g])
+        if refbind.available():
+            cbp = os.path.join(str(tmp_path), "cb.dat")
+            T.write_codebook(cbp, cb)
+            R = refbind.RefMatcher(cbp)
+            lp = os.path.join(str(tmp_path), "l.dat")
+            T.write_template(lp, latents[0])
+            lh, _ = R.load_latent(lp)
+            for g, r in enumerate(rolled):
+                rp = os.path.join(str(tmp_path), f"r{g}.dat")
+                T.write_template(rp, r)
+                rh, rc = R.load_rolled(rp)
+                assert rc == 0
+                _, comp, fin = R.score_pair(lh, rh)
+                assert np.array_equal(out["components"][0, g], comp) and out["scores"][0, g] == fin
+                _, want = R.correspondences(lh, rh)
+                for s in range(3):
+                    assert np.array_equal(got[g][s], want[s]), (g, s)
+            R.close()
+    finally:
+        m.close()
