@@ -76,7 +76,8 @@ __device__ __forceinline__ bool pair_may_connect(float2 la, float2 lb, float2 ra
         // once every |dx|, |dy| is below 50 (:1257).  Tested with 3.625 (the table entries are rounded to fp32,
         // relative 6e-8 on values <= 1110; t*t and 4*s1*s2 round with relative 6e-8 on values whose exact
         // versions differ by > 1e-5 relative whenever the two constants matter): never rejects a connected pair.
-        if (fmaxf(fmaxf(fabsf(dx1), fabsf(dx2)), fmaxf(fabsf(dy1), fabsf(dy2))) >= (float)kTableN) return false;
+        // (the |dx|, |dy| < 50 condition of :1257 is left to the exact entry: pair_h returns 0 for such pairs, and on
+        //  the reference's <= 50 x 50 block grids it never fails, so testing it here only costs instructions)
         const float u = fmaxf(fmaf(s1 + s2, 0.5f, -1.8125f), 0.0f);  // (s1 + s2 - 3.625) / 2, exact
         return u * u <= s1 * s2;
     } else {
