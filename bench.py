@@ -368,7 +368,7 @@ def run_b200_arm(args):
                      "pipe (ncu: 77 % busy in total)"}],
         "kernel_ms_per_step": {n: float(v) for n, v in zip(names, stage_ms[:8])},
         "kernel_ms_note": "per-kernel CUDA-event durations from two extra steps with all kernels serialised on one stream "
-                          "(lafis_set_streams(1)); the timed region overlaps the texture chain with the minutiae chain on "
+                          "(lafis_set_streams(1)); with several pipeline chunks the timed region overlaps the texture chain with the minutiae chain on "
                           "two streams, where the same intervals measure (ms): "
                           + ", ".join(f"{n}={float(v):.1f}" for n, v in zip(names, overlapped_ms[:8])),
     }

@@ -283,8 +283,10 @@ typedef struct {
                                  by the HBM-resident kernels (same results, slower) */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
-/* 2 (default): the texture chain runs on a second CUDA stream concurrently with the minutiae chain;
- * 1: every kernel on one stream, serialised - per-kernel times in lafis_stats are then exclusive. */
+/* 2 (default): when a match runs in several pipeline chunks the texture chain runs on a second CUDA stream
+ * concurrently with the minutiae chain (a single-chunk match is serialised: its kernels are issue-bound and gain
+ * nothing from sharing the SMs); 1: every kernel on one stream always - per-kernel times in lafis_stats are then
+ * exclusive. */
 LAFIS_API int lafis_set_streams(lafis_ctx* ctx, int n_streams);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */
 
