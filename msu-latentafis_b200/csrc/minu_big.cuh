@@ -90,8 +90,11 @@ __global__ void __launch_bounds__(256) minu_big_sim_kernel(MinuBigParams P) {
     }
 }
 
+// floats of the row / column sums, rounded so that the histogram behind them (re-used for 64-bit sort keys) stays
+// 16-byte aligned
+__host__ __device__ inline int minu_big_sum_floats(int max_nL, int max_np) { return (max_nL + max_np + 3) & ~3; }
 __host__ __device__ inline size_t minu_big_select_smem_bytes(int max_nL, int max_np) {
-    return sizeof(float) * ((size_t)max_nL + max_np) + sizeof(int) * kSelBins + sizeof(int) * kSelMaxCand + 16;
+    return sizeof(float) * (size_t)minu_big_sum_floats(max_nL, max_np) + sizeof(int) * kSelBins + sizeof(int) * kSelMaxCand + 16;
 }
 
 // row / column sums of S in the reference's order (matcher.cpp:455-456 through the Eigen stand-in: ascending index)
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kSelThreads) minu_big_select_kernel(MinuBigPar
     }
     float* lsum = reinterpret_cast<float*>(smem);          // [max_nL]
     float* rsum = lsum + P.max_nL;                          // [max_np]
-    int* hist = reinterpret_cast<int*>(rsum + P.max_np);    // [1024]
+    int* hist = reinterpret_cast<int*>(lsum + minu_big_sum_floats(P.max_nL, P.max_np));  // [1024]
     int* cand_e = hist + kSelBins;                          // [kSelMaxCand]
     __shared__ int s_ncand, s_npos, s_flag;
     __shared__ float s_thr;

@@ -213,3 +213,17 @@ def test_correspondences_of_an_oversized_pair(pkg, built, golden, tmp_path):
             R.close()
     finally:
         m.close()
+
+
+def test_oversized_templates_across_pipeline_chunks(pkg, built, golden, oracle, monkeypatch):
+    """The oversized-pair work list is built per pipeline chunk and per latent of a batch: a tiny work budget
+    (several chunks, two streams) and a batch of two latents, one of them oversized itself, against the oracle."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    sizes = [(60, 80), (330, 80), (70, 90), (50, 70), (410, 60), (90, 75), (65, 85), (500, 50), (80, 64)]
+    raws = [T.synth_rolled_raw(3600 + k, n_minu=nm, n_tex=nt) for k, (nm, nt) in enumerate(sizes)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(92, raws[4], n_minu=60, n_tex_pts=40), T.synth_latent(93, raws[7], n_minu=135, n_tex_pts=30)]
+    monkeypatch.setenv("LAFIS_WORK_BYTES", "1500000")
+    st = _run(pkg, cb, latents, rolled, oracle)
+    assert st["minu_big_jobs"] == 3 * 9 + 3 * 3   # the oversized latent against everything + the other against 3 templates
