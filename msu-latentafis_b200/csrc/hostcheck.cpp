@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "dat_format.h"
+#include "minu_plan.h"
 #include "exact_math.h"
 #include "stdsort_emul.h"
 
@@ -97,5 +98,18 @@ int hc_write_latent(const char* path, int h, int w, int blkH, int blkW, int n_mi
         at += n;
     }
     return write_latent_dat(path, h, w, blkH, blkW, minu, tex);
+}
+// the per-call tile plan of the fast minutiae kernels (minu_plan.h)
+void hc_plan_minu(int max_slot_n, int max_nR, const unsigned short* h_n, long n, long* out) {
+    const MinuPlan p = plan_minu(max_slot_n, max_nR, h_n, (size_t)n);
+    out[0] = p.l_cap;
+    out[1] = p.r_cap;
+    out[2] = p.b_double;
+    out[3] = p.efficient ? 1 : 0;
+    out[4] = p.slow_dense ? 1 : 0;
+    out[5] = (long)p.sim_smem;
+    out[6] = (long)p.sel_smem;
+    out[7] = (long)p.slow_smem;
+    out[8] = (long)p.job_stride;
 }
 }

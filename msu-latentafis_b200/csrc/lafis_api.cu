@@ -23,6 +23,7 @@
 #include "graph_prune.cuh"
 #include "graph_sparse.cuh"
 #include "minu_big.cuh"
+#include "minu_plan.h"
 #include "minu_sim.cuh"
 #include "misc_kernels.cuh"
 #include "tex_rowmax.cuh"
@@ -34,7 +35,6 @@ using namespace lafis;
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kMaxDynSmem = 227 * 1024 - 1024;  // kernels also hold a little static shared memory
 
 template <typename T>
 struct DevBuf {
@@ -257,63 +257,6 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     }
     *out = c;
     return LAFIS_OK;
-}
-
-// Shared-memory geometry of the fast minutiae kernels (minu_sim.cuh) for a latent batch and a gallery.  They take
-// latent slots of <= l_cap and gallery templates of <= r_cap minutiae; everything larger goes to minu_big.cuh.
-struct MinuPlan {
-    int l_cap = 1, r_cap = 4;
-    int maxL = 1, maxNp = 4;
-    int a_slot_stride = 0, b_buf_stride = 0, b_double = 1;
-    size_t sim_smem = 0, sel_smem = 0, slow_smem = 0, job_stride = 0;
-    bool slow_dense = false;
-    bool efficient = false;  // double-buffered similarity kernel and four selection CTAs per SM
-};
-constexpr int kFastMaxL = 128;  // three resident latent blocks of 128 minutiae are 148 KB of shared memory
-
-bool minu_plan_fill(MinuPlan& p, int L, int Np) {
-    p.maxL = L;
-    p.maxNp = Np;
-    const int maxLp = (L + 3) & ~3;
-    p.a_slot_stride = 96 * maxLp + 16;
-    p.b_buf_stride = 96 * Np + 160;
-    p.b_double = minu_sim_smem_bytes(p.a_slot_stride, p.b_buf_stride, 1) <= (size_t)kMaxDynSmem ? 1 : 0;
-    p.sim_smem = minu_sim_smem_bytes(p.a_slot_stride, p.b_buf_stride, p.b_double);
-    p.sel_smem = minu_select_smem_bytes(L, Np);
-    // the dense key copy enables the block-parallel introsort replay; one CTA per SM is enough for this rare path
-    p.slow_dense = minu_select_slow_smem_bytes(L, Np, true) <= (size_t)kMaxDynSmem;
-    p.slow_smem = minu_select_slow_smem_bytes(L, Np, p.slow_dense);
-    p.job_stride = (size_t)L * Np;
-    p.efficient = p.b_double && 4 * (p.sel_smem + 2048) <= (size_t)228 * 1024;
-    p.l_cap = L;
-    p.r_cap = Np;
-    return p.sim_smem <= (size_t)kMaxDynSmem && p.slow_smem <= (size_t)kMaxDynSmem && p.sel_smem <= (size_t)kMaxDynSmem &&
-           (size_t)L * Np < 65536;
-}
-
-// max_nR: largest template among the n templates whose minutiae counts are in h_n (may be NULL)
-MinuPlan plan_minu(int max_slot_n, int max_nR, const uint16_t* h_n, size_t n) {
-    MinuPlan p;
-    const int L = std::min(std::max(1, max_slot_n), kFastMaxL);
-    int Np = std::max(4, (max_nR + 3) & ~3);
-    while (Np > 4 && !minu_plan_fill(p, L, Np)) Np -= 4;
-    minu_plan_fill(p, L, Np);
-    if (!p.efficient && h_n && n > 0) {
-        // one outsized template must not push the whole gallery onto the slow geometry: when at most 0.5 % of the
-        // templates exceed the largest efficient tile, they are the ones that go to the big-pair kernels
-        MinuPlan e;
-        int Ne = Np;
-        while (Ne > 4) {
-            if (minu_plan_fill(e, L, Ne) && e.efficient) break;
-            Ne -= 4;
-        }
-        if (Ne > 4 && Ne < Np) {
-            size_t big = 0;
-            for (size_t i = 0; i < n; ++i) big += h_n[i] > Ne;
-            if (big * 200 <= n) p = e;
-        }
-    }
-    return p;
 }
 
 // Everything a packed gallery needs on the host before the device re-layout.

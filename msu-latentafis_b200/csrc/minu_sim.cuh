@@ -28,14 +28,13 @@
 // (stdsort_emul.h).  The output carries the RAW similarity (:486).
 #pragma once
 #include "device_common.cuh"
+#include "minu_plan.h"
 #include "stdsort_emul.h"
 
 namespace lafis {
 
 constexpr int kSimThreads = 512;
 constexpr int kSelThreads = 384;  // 12 warps per job, 4 jobs per SM (shared memory): 48 of 64 warp slots
-constexpr int kSelMaxCand = 512;  // sorted in the histogram's 4 KB (512 x 8 B)
-constexpr int kSelBins = 1024;  // 64 bins per binade over [2^-16, 1): float bits >> 17, offset; smaller values share bin 0
 constexpr uint32_t kSelBinBase = (127u - 16u) << 6;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -70,9 +69,6 @@ struct MinuSimParams {
     size_t job_stride;
 };
 
-__host__ __device__ inline size_t minu_sim_smem_bytes(int a_slot_stride, int b_buf_stride, int b_double) {
-    return sizeof(float) * ((size_t)3 * a_slot_stride + (size_t)(b_double ? 2 : 1) * b_buf_stride);
-}
 
 // One warp tile of S = max(0, A.B^T): rows i0..i0+7 of this thread (16 per warp) and NC columns per thread,
 // 16 lanes across: NC = 8 is the 128-column tile (columns jbase + {lj*4..+3, 64+lj*4..+3}); the other widths
@@ -369,10 +365,6 @@ struct MinuSelectParams {
     int* slow_jobs;
 };
 
-__host__ __device__ inline size_t minu_select_smem_bytes(int max_nL, int max_np) {
-    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(int) * kSelBins +
-           sizeof(int) * kSelMaxCand + 16;
-}
 
 // the reference's normalised similarity, matcher.cpp:467: float sums, "+0.000001" promotes the
 // denominator and the division to double, the quotient is narrowed to float
@@ -585,10 +577,6 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
 // Jobs whose order depends on how libstdc++'s introsort permutes equal keys.
 // `dense`: a second, densely packed copy of the keys (no index arithmetic in the replay's comparator); large
 // templates that cannot afford it compare through the strided copy.
-__host__ __device__ inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np, bool dense) {
-    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) +
-           (sizeof(uint16_t) + (dense ? sizeof(uint32_t) : 0)) * (size_t)max_nL * max_np + 16;
-}
 
 __global__ void __launch_bounds__(kSelThreads) minu_select_slow_kernel(MinuSelectParams P, unsigned long long* replay_count) {
     extern __shared__ __align__(128) unsigned char smem[];
