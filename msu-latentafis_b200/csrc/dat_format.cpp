@@ -312,6 +312,27 @@ int read_codebook(const std::string& path, std::vector<float>& cw, int& subs, in
     return 0;
 }
 
+std::string quoted_path(const std::string& p) {
+    std::string out;
+    out.reserve(p.size() + 2);
+    out.push_back('"');
+    for (char ch : p) {
+        if (ch == '"' || ch == '&') out.push_back('&');
+        out.push_back(ch);
+    }
+    out.push_back('"');
+    return out;
+}
+
+void append_score_row(std::string& out, const std::string& quoted, float score) {
+    char num[64];
+    const int n = std::snprintf(num, sizeof num, "%.3f", (double)score);
+    out.append(quoted);
+    out.push_back(',');
+    out.append(num, (size_t)(n > 0 ? n : 0));
+    out.push_back('\n');
+}
+
 std::vector<std::string> list_dat_files(const std::string& dir) {
     std::vector<std::string> out;
     std::error_code ec;

@@ -61,6 +61,14 @@ int write_latent_dat(const std::string& path, int h, int w, int blkH, int blkW, 
 // u16 subs, u16 clusters, u16 sub_dim, f32[subs][clusters][sub_dim]; returns 0 or a negative LAFIS_ERR_*
 int read_codebook(const std::string& path, std::vector<float>& codewords, int& subs, int& clusters, int& sub_dim);
 
+// A path as the reference prints it into its score files: boost::filesystem's stream inserter
+// (matcher.cpp:202 `output << rolled_template_files[j]`), i.e. boost::io::quoted with '&' as the escape character -
+// double quotes around the string, '&' in front of every '"' and '&'.
+std::string quoted_path(const std::string& p);
+// One row of the N-vs-N score file (matcher.cpp:198-205): <quoted path>,<score, fixed, 3 decimals>\n - what
+// `output << path << "," << std::setprecision(3) << std::fixed << score << std::endl` writes, without the flush.
+void append_score_row(std::string& out, const std::string& quoted, float score);
+
 // *.dat entries of a directory in directory-iteration order (matcher.cpp:103-110, :122-130, :227-234)
 std::vector<std::string> list_dat_files(const std::string& dir);
 

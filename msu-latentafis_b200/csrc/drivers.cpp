@@ -122,7 +122,7 @@ LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_templat
     std::vector<int16_t> corr_xy((size_t)3 * LAFIS_MAX_CORR * 4);
     for (int j = 0; j < 24 && j < G; ++j) {
         const fs::path rolled(lafis_gallery_path(ctx, ind[j]));
-        output << std::to_string(j + 1) << rolled << "," << scores[ind[j]] << std::endl;
+        output << std::to_string(j + 1) << quoted_path(rolled.string()) << "," << scores[ind[j]] << std::endl;
         const int gst = lafis_gallery_status(ctx, ind[j]);
         if (gst == LAFIS_TPL_OK || gst == LAFIS_TPL_TRUNCATED) {  // the reference returns before matching an empty print (:388-391)
             int counts[3] = {0, 0, 0};
@@ -264,6 +264,8 @@ LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, c
     // batches bounded by the size of the host score matrix (256 MB)
     const int batch = std::max(1, std::min(n, (int)(((size_t)64 << 20) / (size_t)std::max(G, 1))));
     std::vector<float> scores;
+    std::vector<std::string> quoted;  // gallery paths as the score files print them, built once
+    std::string rows;
     for (int b0 = 0; b0 < n; b0 += batch) {
         const int nb = std::min(batch, n - b0);
         std::vector<const char*> ptrs(nb);
@@ -305,10 +307,15 @@ LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, c
                           << std::endl;
                 continue;
             }
-            std::ofstream output(out_name);
-            for (int j = 0; j < G; ++j)
-                output << fs::path(lafis_gallery_path(ctx, j)) << "," << std::setprecision(3) << std::fixed
-                       << scores[(size_t)i * G + j] << std::endl;
+            // one buffered write per latent (the reference flushes every row: 10^6 system calls per file at scale)
+            if (quoted.empty() && G > 0) {
+                quoted.resize(G);
+                for (int j = 0; j < G; ++j) quoted[j] = quoted_path(lafis_gallery_path(ctx, j));
+            }
+            rows.clear();
+            for (int j = 0; j < G; ++j) append_score_row(rows, quoted[j], scores[(size_t)i * G + j]);
+            std::ofstream output(out_name, std::ios::binary);
+            output.write(rows.data(), (std::streamsize)rows.size());
         }
         lafis_latents_free(L);
     }

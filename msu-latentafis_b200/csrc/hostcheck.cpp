@@ -112,4 +112,11 @@ void hc_plan_minu(int max_slot_n, int max_nR, const unsigned short* h_n, long n,
     out[7] = (long)p.slow_smem;
     out[8] = (long)p.job_stride;
 }
+// rows of the N-vs-N score file as the driver writes them; returns the length (the buffer holds at most cap bytes)
+long hc_format_score_rows(const char* const* paths, const float* scores, int n, char* out, long cap) {
+    std::string buf;
+    for (int i = 0; i < n; ++i) append_score_row(buf, quoted_path(paths[i]), scores[i]);
+    std::memcpy(out, buf.data(), std::min<size_t>(buf.size(), (size_t)cap));
+    return (long)buf.size();
+}
 }

@@ -139,3 +139,23 @@ def test_latent_writer_is_byte_identical_to_the_python_writer(pkg, hc, tmp_path)
         _, rc = R.load_latent(a)
         assert rc == 0
         R.close()
+
+
+def test_score_rows_are_what_the_reference_stream_writes(hc):
+    """N-vs-N score file rows (matcher.cpp:198-205): "<path>",<score %.3f> per gallery file, the path quoted the way
+    boost::filesystem's inserter does it ('&' escapes '"' and '&'), the score as iostream's fixed / setprecision(3)
+    prints a float.  The driver formats whole files in one buffer instead of flushing every row."""
+    rng = np.random.default_rng(3)
+    paths = ["/data/rolled/0001.dat", "rel/dir with space/a.dat", 'odd"quote&amp.dat', "/x/y\\z.dat", ""]
+    paths += [f"/g/{i:07d}.dat" for i in range(300)]
+    scores = np.concatenate([np.array([-1.0, 0.0, -0.0, 0.0005, 0.0015, 2.5e-4, 1234567.875, 9.9995, 1e-9, -1e-9], np.float32),
+                             rng.uniform(0, 40, len(paths) - 10).astype(np.float32)])
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    hc.hc_format_score_rows.restype = C.c_long
+    n = hc.hc_format_score_rows(arr, scores.ctypes.data_as(C.c_void_p), len(paths), buf, cap)
+    got = buf.raw[:n].decode()
+    want = "".join('"' + p.replace("&", "&&").replace('"', '&"') + '",' + "%.3f" % float(s) + "\n" for p, s in zip(paths, scores))
+    assert got == want
+    assert '"/data/rolled/0001.dat",-1.000\n' in got and ',-0.000\n' in got
