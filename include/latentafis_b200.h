@@ -269,7 +269,7 @@ typedef struct {
     float last_match_ms;      /* device time of the last lafis_match*, CUDA events */
     float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events between the
                                  launches): 0 tex_rowmax, 1 minu_sim, 2 minu_select, 3 graph_minu_sparse,
-                                 4 graph_tex (sparse + dense), 5 fuse + rank lists, 6 minu_select_slow,
+                                 4 graph_tex (sparse + dense), 5 fuse + rank lists, 6 minu_select_slow (+ the oversized-pair kernels),
                                  7 graph_minu_dense.  The texture chain (0, 4) runs on a second stream
                                  concurrently with the others, so the intervals overlap. */
     /* cumulative exactness bookkeeping since the context was created */
