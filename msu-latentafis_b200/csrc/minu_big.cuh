@@ -113,7 +113,7 @@ __device__ __forceinline__ void big_sums(const float* __restrict__ S, int nL, in
 }
 
 __global__ void __launch_bounds__(kSelThreads) minu_big_select_kernel(MinuBigParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kSelThreads / 32;
     const BigJob b = big_job(P, blockIdx.x);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kSelThreads) minu_big_select_kernel(MinuBigPar
 }
 
 __global__ void __launch_bounds__(kSelThreads) minu_big_slow_kernel(MinuBigParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kSelThreads / 32;
     float* lsum = reinterpret_cast<float*>(smem);
