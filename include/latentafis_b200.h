@@ -131,9 +131,13 @@ LAFIS_API int lafis_latents_from_packed(lafis_ctx* ctx, const lafis_packed_laten
 LAFIS_API int lafis_latents_count(const lafis_latents* l);
 LAFIS_API uint64_t lafis_latents_bytes(const lafis_latents* l); /* bytes one host-to-device staging copy moves */
 LAFIS_API int lafis_latents_status(const lafis_latents* l, int q); /* LAFIS_OK, LAFIS_LATENT_EMPTY, LAFIS_ERR_LATENT_LAYOUT */
+LAFIS_API int lafis_latents_minu_templates(const lafis_latents* l, int q); /* non-empty minutiae templates in the file
+                                                                              (m_nrof_minu_templates, matcher.cpp:403) */
 LAFIS_API void lafis_latents_free(lafis_latents* l);
 /* pre-stage the batch in HBM so that a following lafis_match() performs no host-to-device copy */
 LAFIS_API int lafis_latents_make_resident(lafis_ctx* ctx, lafis_latents* l);
+/* A latent batch may be used with any context of the process (non-resident batches are staged per match) and may
+ * be freed before or after the context it was created on. */
 
 /* ---- the hot path: replaces the omp loop of One2List_matching / List2List_matching
  *      (matcher.cpp:168-190, :273-295) = One2One_matching_selected_templates (:376-417) for every
@@ -172,6 +176,52 @@ LAFIS_API int lafis_merge_hits(const lafis_hit* shard_hits, int n_latents, int n
  * Enqueued on the context's stream; n_lists * topk <= 4096. */
 LAFIS_API int lafis_merge_hits_device(lafis_ctx* ctx, const void* d_gathered, int n_latents, int n_lists, int topk,
                                       void* d_out);
+
+/* ---- multi-GPU: the gallery loop of One2List_matching / List2List_matching (matcher.cpp:168-190,
+ *      :273-295) sharded over ranks by contiguous gallery index ranges (lafis_gallery_load_*(rank, world)), the rank
+ *      list of :306-309 rebuilt from the shards' lists with ONE ncclAllGather + lafis_merge_hits_device, and - for the
+ *      score rows of :198-205 - the shards' score blocks gathered to one rank.  A context joins a communicator with
+ *      lafis_comm_init: rank 0 obtains an id with lafis_comm_unique_id and hands it to the other ranks (one process
+ *      per GPU, any launcher), or lafis_group_create does all of it for several devices of one process.  NCCL is
+ *      bound at run time (libnccl.so.2); these calls fail with LAFIS_ERR_CUDA when it is absent. ---- */
+#define LAFIS_COMM_ID_BYTES 128
+LAFIS_API int lafis_comm_unique_id(void* id_out /* [LAFIS_COMM_ID_BYTES] */);
+LAFIS_API int lafis_comm_init(lafis_ctx* ctx, const void* id, int rank, int world); /* collective: every rank calls */
+LAFIS_API int lafis_comm_rank(const lafis_ctx* ctx);  /* -1 without a communicator */
+LAFIS_API int lafis_comm_world(const lafis_ctx* ctx); /* 1 without a communicator */
+LAFIS_API void lafis_comm_destroy(lafis_ctx* ctx);
+LAFIS_API int lafis_comm_nccl_version(void);          /* e.g. 22703; 0 when NCCL is not loadable */
+/* collective: gallery templates over all shards (>= 0) or a negative status; the optional arrays [world] receive
+ * every shard's first global index and size */
+LAFIS_API int lafis_gallery_total(lafis_ctx* ctx, uint32_t* shard_base_out, uint32_t* shard_n_out);
+/* The sharded hot path; collective, every rank passes the same latent batch, topk, gather_scores and root.
+ *   hits          every rank: [n_latents * topk] GLOBAL rank lists (may be NULL: no lists)
+ *   gather_scores != 0: the fused scores of all shards are gathered to `root`
+ *   all_scores    root only: [n_latents * G_total] rows in global gallery order; ignored elsewhere */
+LAFIS_API int lafis_match_sharded(lafis_ctx* ctx, lafis_latents* latents, int topk, lafis_hit* hits, int gather_scores,
+                                  float* all_scores, int root);
+/* same, the merged global rank lists stay in HBM (valid until the next match on this context) */
+LAFIS_API int lafis_match_sharded_device(lafis_ctx* ctx, lafis_latents* latents, int topk, const void** d_hits);
+
+/* several devices of one process: one context per device, joined by a communicator; a latent batch created on any
+ * of the contexts serves all of them */
+typedef struct lafis_group lafis_group;
+LAFIS_API int lafis_group_create(const char* codebook_path, const int* devices /* NULL: 0..n-1 */, int n_devices,
+                                 lafis_group** out);
+LAFIS_API void lafis_group_destroy(lafis_group* group);
+LAFIS_API int lafis_group_size(const lafis_group* group);
+LAFIS_API lafis_ctx* lafis_group_ctx(lafis_group* group, int i);
+LAFIS_API const char* lafis_group_last_error(const lafis_group* group);
+LAFIS_API int lafis_group_gallery_load_dir(lafis_group* group, const char* dir);
+LAFIS_API int lafis_group_gallery_load_files(lafis_group* group, const char* const* paths, int n);
+LAFIS_API int lafis_group_gallery_size(const lafis_group* group); /* over all shards */
+/* lafis_match over the sharded gallery: hits [n_latents * topk] global lists, all_scores [n_latents * G_total] */
+LAFIS_API int lafis_group_match(lafis_group* group, lafis_latents* latents, int topk, lafis_hit* hits, float* all_scores);
+/* the two drivers below over the sharded gallery: same files, byte for byte */
+LAFIS_API int lafis_group_one2list_matching(lafis_group* group, const char* latent_template_file, const char* rolled_dir,
+                                            const char* score_path);
+LAFIS_API int lafis_group_list2list_matching(lafis_group* group, const char* latent_dir, const char* rolled_dir,
+                                             const char* score_path);
 
 /* ---- drivers with the reference's score-file formats (SURVEY.md §8b "Score files") ----
  *      lafis_one2list_matching  replaces PQ::Matcher::One2List_matching,  matcher.cpp:216-337:
@@ -281,6 +331,9 @@ typedef struct {
     uint64_t tex_templates;   /* ... (warp, template) visits in total */
     uint64_t minu_big_jobs;   /* (latent, template, minutiae slot) jobs too large for the shared-memory tiles, scored
                                  by the HBM-resident kernels (same results, slower) */
+    uint64_t graph_minu_dense_jobs; /* minutiae pruning jobs whose consistency graph did not fit the sparse kernel
+                                       (mated or near-duplicate prints): dense kernel, same result, ~50 us each */
+    uint64_t graph_tex_dense_jobs;  /* the same for the texture component */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 /* 2 (default): when a match runs in several pipeline chunks the texture chain runs on a second CUDA stream

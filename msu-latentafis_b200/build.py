@@ -54,9 +54,17 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
     run = lambda cmd: subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     so = lib_path()
     if force or _newer(so, srcs):
-        run([_nvcc()] + NVCC_FLAGS + ["-shared", os.path.join(CSRC, "lafis_api.cu"), os.path.join(CSRC, "dat_format.cpp"),
-                                      os.path.join(CSRC, "drivers.cpp"),
-                                      "-o", so])
+        # every translation unit as CUDA (-x cu: they share lafis_internal.h, which carries device declarations), in
+        # parallel; sharded.cu needs <nccl.h> for types only - NCCL itself is bound at run time (dlopen), so no -lnccl
+        from concurrent.futures import ThreadPoolExecutor
+        obj_dir = os.path.join(HERE, "build")
+        os.makedirs(obj_dir, exist_ok=True)
+        units = ["lafis_api.cu", "sharded.cu", "dat_format.cpp", "drivers.cpp"]
+        objs = [os.path.join(obj_dir, u.rsplit(".", 1)[0] + ".o") for u in units]
+        with ThreadPoolExecutor(len(units)) as ex:
+            list(ex.map(lambda uo: run([_nvcc()] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, uo[0]), "-o", uo[1]]),
+                        zip(units, objs)))
+        run([_nvcc()] + NVCC_FLAGS + ["-shared"] + objs + ["-ldl", "-o", so])
     hc = os.path.join(LIB, "libhostcheck.so")
     if force or _newer(hc, srcs):
         run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",

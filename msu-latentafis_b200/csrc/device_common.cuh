@@ -46,6 +46,14 @@ struct DeviceLatents {
     int* status = nullptr;          // [n] LAFIS_OK / LAFIS_LATENT_EMPTY / LAFIS_ERR_LATENT_LAYOUT
 };
 
+constexpr int kMergeCap = 4096;    // rank-list entries one merge CTA sorts (= kTopkChunk, misc_kernels.cuh)
+
+// one rank-list entry in HBM; same layout as lafis_hit
+struct HitDev {
+    float score;
+    uint32_t index;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Block-wide bitonic sort of np2 (a power of two, >= 32, <= NT * KPT) 64-bit keys in shared memory, descending.

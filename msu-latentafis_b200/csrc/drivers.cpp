@@ -18,23 +18,106 @@
 #include <string>
 #include <vector>
 
-#include "../../include/latentafis_b200.h"
 #include "dat_format.h"
+#include "lafis_internal.h"
 
 namespace fs = std::filesystem;
 using namespace lafis;
 
 namespace {
 
-// the gallery already resident on `ctx` is reused when it was loaded from the same directory
-struct DirCache {
-    lafis_ctx* ctx = nullptr;
-    std::string dir;
+// What the drivers need from "a matcher": one context, or a group of contexts over a sharded gallery.
+struct Engine {
+    virtual ~Engine() {}
+    virtual int load_files(const std::vector<const char*>& ptrs) = 0;
+    virtual bool has_dir(const std::string& dir) const = 0;  // the resident gallery was loaded from `dir`
+    virtual void set_dir(const std::string& dir) = 0;
+    virtual int gallery_size() const = 0;
+    virtual const char* gallery_path(int j) const = 0;
+    virtual int gallery_status(int j) const = 0;
+    virtual int gallery_minutiae(int j) = 0;                 // minutiae of template j (0: no minutiae template)
+    virtual lafis_ctx* latents_ctx() = 0;
+    virtual int match_scores(lafis_latents* L, float* scores) = 0;
+    virtual int correspondences(lafis_latents* L, int q, int j, int16_t* xy, int* counts) = 0;
+    virtual const char* last_error() const = 0;
 };
-DirCache g_cache;
 
-int ensure_gallery(lafis_ctx* ctx, const std::string& dir, bool announce) {
-    if (g_cache.ctx == ctx && g_cache.dir == dir && lafis_gallery_size(ctx) > 0) return LAFIS_OK;
+struct SingleEngine : Engine {
+    lafis_ctx* c;
+    explicit SingleEngine(lafis_ctx* ctx) : c(ctx) {}
+    int load_files(const std::vector<const char*>& p) override { return lafis_gallery_load_files(c, p.data(), (int)p.size(), 0, 1); }
+    // the association lives in the context and is dropped by everything that replaces the gallery (free_gallery)
+    bool has_dir(const std::string& dir) const override {
+        return c->gallery_set && c->gallery_dir == dir && c->gallery_dir_shards == 1 && c->gal.n > 0;
+    }
+    void set_dir(const std::string& dir) override {
+        c->gallery_dir = dir;
+        c->gallery_dir_shard = 0;
+        c->gallery_dir_shards = 1;
+    }
+    int gallery_size() const override { return lafis_gallery_size(c); }
+    const char* gallery_path(int j) const override { return lafis_gallery_path(c, j); }
+    int gallery_status(int j) const override { return lafis_gallery_status(c, j); }
+    int gallery_minutiae(int j) override { return (j >= 0 && j < (int)c->h_minu_n.size()) ? c->h_minu_n[j] : 0; }
+    lafis_ctx* latents_ctx() override { return c; }
+    int match_scores(lafis_latents* L, float* scores) override { return lafis_match(c, L, 0, nullptr, scores, nullptr); }
+    int correspondences(lafis_latents* L, int q, int j, int16_t* xy, int* counts) override {
+        return lafis_correspondences(c, L, q, j, xy, counts);
+    }
+    const char* last_error() const override { return lafis_last_error(c); }
+};
+
+struct GroupEngine : Engine {
+    lafis_group* g;
+    explicit GroupEngine(lafis_group* grp) : g(grp) {}
+    int shard_of(int j) const {
+        int r = 0;
+        while (r + 1 < (int)g->ctx.size() && (uint32_t)j >= g->base[r + 1]) ++r;
+        return r;
+    }
+    int load_files(const std::vector<const char*>& p) override { return lafis_group_gallery_load_files(g, p.data(), (int)p.size()); }
+    bool has_dir(const std::string& dir) const override {
+        const int w = (int)g->ctx.size();
+        for (int i = 0; i < w; ++i) {
+            const lafis_ctx* c = g->ctx[i];
+            if (!c->gallery_set || c->gallery_dir != dir || c->gallery_dir_shard != i || c->gallery_dir_shards != w) return false;
+        }
+        return lafis_group_gallery_size(g) > 0;
+    }
+    void set_dir(const std::string& dir) override {
+        for (size_t i = 0; i < g->ctx.size(); ++i) {
+            g->ctx[i]->gallery_dir = dir;
+            g->ctx[i]->gallery_dir_shard = (int)i;
+            g->ctx[i]->gallery_dir_shards = (int)g->ctx.size();
+        }
+    }
+    int gallery_size() const override { return lafis_group_gallery_size(g); }
+    const char* gallery_path(int j) const override {
+        const int r = shard_of(j);
+        return lafis_gallery_path(g->ctx[r], j - (int)g->base[r]);
+    }
+    int gallery_status(int j) const override {
+        const int r = shard_of(j);
+        return lafis_gallery_status(g->ctx[r], j - (int)g->base[r]);
+    }
+    int gallery_minutiae(int j) override {
+        const int r = shard_of(j), l = j - (int)g->base[r];
+        const lafis_ctx* c = g->ctx[r];
+        return (l >= 0 && l < (int)c->h_minu_n.size()) ? c->h_minu_n[l] : 0;
+    }
+    lafis_ctx* latents_ctx() override { return g->ctx[0]; }
+    int match_scores(lafis_latents* L, float* scores) override { return lafis_group_match(g, L, 0, nullptr, scores); }
+    int correspondences(lafis_latents* L, int q, int j, int16_t* xy, int* counts) override {
+        const int r = shard_of(j);  // on the device that holds the template
+        const int rc = lafis_correspondences(g->ctx[r], L, q, j - (int)g->base[r], xy, counts);
+        if (rc < 0) g->err = lafis_last_error(g->ctx[r]);
+        return rc;
+    }
+    const char* last_error() const override { return lafis_group_last_error(g); }
+};
+
+int ensure_gallery(Engine& E, const std::string& dir, bool announce) {
+    if (E.has_dir(dir)) return LAFIS_OK;
     std::vector<std::string> files = list_dat_files(dir);
     if (announce)
         for (const std::string& f : files) std::cout << "rolled template file" << fs::path(f) << std::endl;
@@ -44,109 +127,48 @@ int ensure_gallery(lafis_ctx* ctx, const std::string& dir, bool announce) {
     }
     std::vector<const char*> ptrs(files.size());
     for (size_t i = 0; i < files.size(); ++i) ptrs[i] = files[i].c_str();
-    int rc = lafis_gallery_load_files(ctx, ptrs.data(), (int)ptrs.size(), 0, 1);
-    if (rc == LAFIS_OK) {
-        g_cache.ctx = ctx;
-        g_cache.dir = dir;
-    }
+    const int rc = E.load_files(ptrs);
+    if (rc == LAFIS_OK) E.set_dir(dir);
     return rc;
 }
+
+int one2list(Engine& E, const char* latent_template_file, const char* rolled_dir, const char* score_path);
+int list2list(Engine& E, const char* latent_dir, const char* rolled_dir, const char* score_path);
 
 }  // namespace
 
 extern "C" {
 
 LAFIS_API void lafis_forget_gallery_dir(lafis_ctx* ctx) {
-    if (g_cache.ctx == ctx) g_cache = DirCache();
+    if (ctx) ctx->gallery_dir.clear();
 }
 
 LAFIS_API int lafis_one2list_matching(lafis_ctx* ctx, const char* latent_template_file, const char* rolled_dir,
                                       const char* score_path) {
     if (!ctx || !latent_template_file || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
-    const fs::path latent_file(latent_template_file);
-    const std::string score_file = std::string(score_path) + latent_file.stem().string() + ".csv";
-    int rc = ensure_gallery(ctx, rolled_dir, false);
-    if (rc != LAFIS_OK) return rc;
-    const int G = lafis_gallery_size(ctx);
-    const auto t0 = std::chrono::high_resolution_clock::now();
-    std::cout << "Latent Query: " << latent_file << std::endl;
-    std::cout << "Gallery size: " << G << std::endl;
+    SingleEngine E(ctx);
+    return one2list(E, latent_template_file, rolled_dir, score_path);
+}
 
-    lafis_latents* L = nullptr;
-    const char* lp = latent_template_file;
-    rc = lafis_latents_load_files(ctx, &lp, 1, &L);
-    if (rc != LAFIS_OK) return rc;
-    const int st = lafis_latents_status(L, 0);
-    if (st == LAFIS_LATENT_EMPTY) {
-        // matcher.cpp:260-267 writes "0" when the latent holds no template at all; every pair then
-        // returns 1 and the driver exits with 1 (:296-299).  A latent with 1..26 minutiae templates
-        // and no texture template takes the same exit without the file.
-        LatentTemplate T;
-        read_latent_dat(latent_template_file, T);
-        if (T.n_minu_templates <= 0 && T.n_tex_templates <= 0) {
-            std::ofstream output(score_file);
-            output << 0 << std::endl;
-        }
-        std::cout << "Matching failed: latent template is empty. Exiting." << std::endl;
-        lafis_latents_free(L);
-        return LAFIS_LATENT_EMPTY;
-    }
-    if (st != LAFIS_OK) {
-        lafis_latents_free(L);
-        return st;
-    }
-    std::vector<float> scores((size_t)G, -1.0f);
-    rc = lafis_match(ctx, L, 0, nullptr, scores.data(), nullptr);
-    if (rc != LAFIS_OK) {
-        lafis_latents_free(L);
-        return rc;
-    }
-    for (int j = 0; j < G; ++j)
-        if (scores[j] == -1.0f && lafis_gallery_status(ctx, j) != LAFIS_TPL_OK &&
-            lafis_gallery_status(ctx, j) != LAFIS_TPL_TRUNCATED)
-            std::cout << "Comparison failed: rolled template is empty. Skipping." << std::endl;
+LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
+                                       const char* score_path) {
+    if (!ctx || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+    SingleEngine E(ctx);
+    return list2list(E, latent_dir, rolled_dir, score_path);
+}
 
-    // rank list: the reference's own call, std::sort with (scores[a] > scores[b]) (matcher.cpp:306-309)
-    std::vector<int> ind((size_t)G);
-    std::iota(ind.begin(), ind.end(), 0);
-    std::sort(ind.begin(), ind.end(), [&](const int& a, const int& b) { return scores[a] > scores[b]; });
-    std::ofstream output(score_file);
-    output << "filename,score" << std::endl;
-    std::cout << "Match Results" << std::endl;
-    std::cout << "----------------" << std::endl;
-    std::cout << "Rank     Filename      Score" << std::endl;
-    // correspondence files of the 24 best (matcher.cpp:322-327, written by :497-505); the reference's prefix
-    // "/LatentAFIS/scores/" is configurable here
-    const char* corr_env = std::getenv("LAFIS_CORR_PATH");
-    const std::string corr_prefix = corr_env ? std::string(corr_env) : std::string(score_path);
-    std::vector<int16_t> corr_xy((size_t)3 * LAFIS_MAX_CORR * 4);
-    for (int j = 0; j < 24 && j < G; ++j) {
-        const fs::path rolled(lafis_gallery_path(ctx, ind[j]));
-        output << std::to_string(j + 1) << quoted_path(rolled.string()) << "," << scores[ind[j]] << std::endl;
-        const int gst = lafis_gallery_status(ctx, ind[j]);
-        if (gst == LAFIS_TPL_OK || gst == LAFIS_TPL_TRUNCATED) {  // the reference returns before matching an empty print (:388-391)
-            int counts[3] = {0, 0, 0};
-            rc = lafis_correspondences(ctx, L, 0, ind[j], corr_xy.data(), counts);
-            if (rc != LAFIS_OK) {
-                lafis_latents_free(L);
-                return rc;
-            }
-            const std::string corr_file = corr_prefix + "corr" + latent_file.stem().string() + "_" + rolled.stem().string();
-            for (int i = 0; i < 3; ++i) {
-                std::ofstream co(corr_file + "_" + std::to_string(i) + ".csv");
-                for (int k = 0; k < counts[i]; ++k) {
-                    const int16_t* e = &corr_xy[((size_t)i * LAFIS_MAX_CORR + k) * 4];
-                    co << e[0] << "," << e[1] << "," << e[2] << "," << e[3] << std::endl;
-                }
-            }
-        }
-        std::cout << std::to_string(j + 1) << "        " << rolled.filename() << "       " << scores[ind[j]] << std::endl;
-    }
-    lafis_latents_free(L);
-    output.close();
-    const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
-    std::cout << "Total matching duration (ms): " << span.count() << std::endl;
-    return LAFIS_OK;
+LAFIS_API int lafis_group_one2list_matching(lafis_group* group, const char* latent_template_file, const char* rolled_dir,
+                                            const char* score_path) {
+    if (!group || !latent_template_file || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+    GroupEngine E(group);
+    return one2list(E, latent_template_file, rolled_dir, score_path);
+}
+
+LAFIS_API int lafis_group_list2list_matching(lafis_group* group, const char* latent_dir, const char* rolled_dir,
+                                             const char* score_path) {
+    if (!group || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+    GroupEngine E(group);
+    return list2list(E, latent_dir, rolled_dir, score_path);
 }
 
 LAFIS_API int lafis_enroll_rolled(lafis_ctx* ctx, const lafis_rolled_features* F, const char* out_path) {
@@ -245,18 +267,112 @@ LAFIS_API int lafis_enroll_latent(lafis_ctx* ctx, const lafis_latent_features* F
     return write_latent_dat(out_path, F->h, F->w, F->blkH, F->blkW, minu, tex) == 0 ? LAFIS_OK : LAFIS_ERR_IO;
 }
 
-LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, const char* rolled_dir,
-                                       const char* score_path) {
-    if (!ctx || !latent_dir || !rolled_dir || !score_path) return LAFIS_ERR_ARG;
+}  // extern "C"
+
+namespace {
+
+int one2list(Engine& E, const char* latent_template_file, const char* rolled_dir, const char* score_path) {
+    lafis_ctx* ctx = E.latents_ctx();
+    const fs::path latent_file(latent_template_file);
+    const std::string score_file = std::string(score_path) + latent_file.stem().string() + ".csv";
+    int rc = ensure_gallery(E, rolled_dir, false);
+    if (rc != LAFIS_OK) return rc;
+    const int G = E.gallery_size();
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    std::cout << "Latent Query: " << latent_file << std::endl;
+    std::cout << "Gallery size: " << G << std::endl;
+
+    lafis_latents* L = nullptr;
+    const char* lp = latent_template_file;
+    rc = lafis_latents_load_files(ctx, &lp, 1, &L);
+    if (rc != LAFIS_OK) return rc;
+    const int st = lafis_latents_status(L, 0);
+    if (st == LAFIS_LATENT_EMPTY) {
+        // matcher.cpp:260-267 writes "0" when the latent holds no template at all; every pair then
+        // returns 1 and the driver exits with 1 (:296-299).  A latent with 1..26 minutiae templates
+        // and no texture template takes the same exit without the file.
+        LatentTemplate T;
+        read_latent_dat(latent_template_file, T);
+        if (T.n_minu_templates <= 0 && T.n_tex_templates <= 0) {
+            std::ofstream output(score_file);
+            output << 0 << std::endl;
+        }
+        std::cout << "Matching failed: latent template is empty. Exiting." << std::endl;
+        lafis_latents_free(L);
+        return LAFIS_LATENT_EMPTY;
+    }
+    if (st != LAFIS_OK) {
+        lafis_latents_free(L);
+        return st;
+    }
+    std::vector<float> scores((size_t)G, -1.0f);
+    rc = E.match_scores(L, scores.data());
+    if (rc != LAFIS_OK) {
+        lafis_latents_free(L);
+        return rc;
+    }
+    for (int j = 0; j < G; ++j)
+        if (scores[j] == -1.0f && E.gallery_status(j) != LAFIS_TPL_OK && E.gallery_status(j) != LAFIS_TPL_TRUNCATED)
+            std::cout << "Comparison failed: rolled template is empty. Skipping." << std::endl;
+
+    // rank list: the reference's own call, std::sort with (scores[a] > scores[b]) (matcher.cpp:306-309)
+    std::vector<int> ind((size_t)G);
+    std::iota(ind.begin(), ind.end(), 0);
+    std::sort(ind.begin(), ind.end(), [&](const int& a, const int& b) { return scores[a] > scores[b]; });
+    std::ofstream output(score_file);
+    output << "filename,score" << std::endl;
+    std::cout << "Match Results" << std::endl;
+    std::cout << "----------------" << std::endl;
+    std::cout << "Rank     Filename      Score" << std::endl;
+    // correspondence files of the 24 best (matcher.cpp:322-327, written by :497-505); the reference's prefix
+    // "/LatentAFIS/scores/" is configurable here
+    const char* corr_env = std::getenv("LAFIS_CORR_PATH");
+    const std::string corr_prefix = corr_env ? std::string(corr_env) : std::string(score_path);
+    std::vector<int16_t> corr_xy((size_t)3 * LAFIS_MAX_CORR * 4);
+    const int latent_nm = lafis_latents_minu_templates(L, 0);
+    for (int j = 0; j < 24 && j < G; ++j) {
+        const fs::path rolled(E.gallery_path(ind[j]));
+        output << std::to_string(j + 1) << quoted_path(rolled.string()) << "," << scores[ind[j]] << std::endl;
+        const int gst = E.gallery_status(ind[j]);
+        // the reference returns before matching an empty print (:388-391) and only enters the minutiae loop when the
+        // rolled print has a minutiae template (:400)
+        if ((gst == LAFIS_TPL_OK || gst == LAFIS_TPL_TRUNCATED) && E.gallery_minutiae(ind[j]) > 0) {
+            int counts[3] = {0, 0, 0};
+            rc = E.correspondences(L, 0, ind[j], corr_xy.data(), counts);
+            if (rc != LAFIS_OK) {
+                lafis_latents_free(L);
+                return rc;
+            }
+            const std::string corr_file = corr_prefix + "corr" + latent_file.stem().string() + "_" + rolled.stem().string();
+            for (int i = 0; i < 3; ++i) {
+                if (latent_nm <= kSelected[i]) continue;  // :403-404: no such latent template, no file
+                std::ofstream co(corr_file + "_" + std::to_string(i) + ".csv");
+                for (int k = 0; k < counts[i]; ++k) {
+                    const int16_t* e = &corr_xy[((size_t)i * LAFIS_MAX_CORR + k) * 4];
+                    co << e[0] << "," << e[1] << "," << e[2] << "," << e[3] << std::endl;
+                }
+            }
+        }
+        std::cout << std::to_string(j + 1) << "        " << rolled.filename() << "       " << scores[ind[j]] << std::endl;
+    }
+    lafis_latents_free(L);
+    output.close();
+    const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
+    std::cout << "Total matching duration (ms): " << span.count() << std::endl;
+    return LAFIS_OK;
+}
+
+int list2list(Engine& E, const char* latent_dir, const char* rolled_dir, const char* score_path) {
+    lafis_ctx* ctx = E.latents_ctx();
     std::vector<std::string> latent_files = list_dat_files(latent_dir);
     for (const std::string& f : latent_files) std::cout << "latent template file" << fs::path(f) << std::endl;
     if (latent_files.empty()) {
         std::cout << "No latent templates found in directory: " << latent_dir << std::endl;
         return LAFIS_ERR_NO_TEMPLATES;
     }
-    int rc = ensure_gallery(ctx, rolled_dir, true);
+    int rc = ensure_gallery(E, rolled_dir, true);
     if (rc != LAFIS_OK) return rc;
-    const int G = lafis_gallery_size(ctx);
+    const int G = E.gallery_size();
     std::cout << "Gallery size: " << G << std::endl;
     const auto t0 = std::chrono::high_resolution_clock::now();
 
@@ -277,7 +393,7 @@ LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, c
         bool any = false;
         for (int i = 0; i < nb; ++i) any = any || lafis_latents_status(L, i) == LAFIS_OK;
         if (any) {
-            rc = lafis_match(ctx, L, 0, nullptr, scores.data(), nullptr);
+            rc = E.match_scores(L, scores.data());
             if (rc != LAFIS_OK) {
                 lafis_latents_free(L);
                 return rc;
@@ -310,7 +426,7 @@ LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, c
             // one buffered write per latent (the reference flushes every row: 10^6 system calls per file at scale)
             if (quoted.empty() && G > 0) {
                 quoted.resize(G);
-                for (int j = 0; j < G; ++j) quoted[j] = quoted_path(lafis_gallery_path(ctx, j));
+                for (int j = 0; j < G; ++j) quoted[j] = quoted_path(E.gallery_path(j));
             }
             rows.clear();
             for (int j = 0; j < G; ++j) append_score_row(rows, quoted[j], scores[(size_t)i * G + j]);
@@ -324,4 +440,4 @@ LAFIS_API int lafis_list2list_matching(lafis_ctx* ctx, const char* latent_dir, c
     return LAFIS_OK;
 }
 
-}  // extern "C"
+}  // namespace

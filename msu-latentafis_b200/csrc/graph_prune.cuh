@@ -273,6 +273,7 @@ struct GraphMinuParams {
     // {latent x, latent y, rolled x, rolled y} and their count - the reference's save_corr output
     short4* corr_out = nullptr;
     int* corr_out_n = nullptr;
+    unsigned long long* dense_jobs_total = nullptr;  // statistics: jobs the dense kernel took over
 };
 
 constexpr int kGraphMinuThreads = 128;
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(kGraphMinuThreads) graph_minu_dense_kernel(Gra
     GraphWork<kTopCorrMinu>& w = *reinterpret_cast<GraphWork<kTopCorrMinu>*>(smem + sizeof(float) * kTopCorrMinu * kTopCorrMinu);
     const int tid = threadIdx.x;
     const int n_jobs = *job_count;
+    if (blockIdx.x == 0 && tid == 0 && P.dense_jobs_total && !P.corr_out) atomicAdd(P.dense_jobs_total, (unsigned long long)n_jobs);
     for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
         const size_t oidx = (size_t)jobs[jb];  // (q * n_chunk + tl) * 3 + slot
         const int slot = (int)(oidx % 3);
@@ -342,6 +344,7 @@ struct GraphTexParams {
     int G;
     float* comp;               // [Q][G][4]; slot 3
     unsigned long long* slow_path_count;
+    unsigned long long* dense_jobs_total = nullptr;  // statistics: jobs the dense kernel took over
 };
 
 constexpr int kGraphTexThreads = 256;
@@ -364,6 +367,7 @@ __global__ void __launch_bounds__(kGraphTexThreads) graph_tex_dense_kernel(Graph
     TexRowWork& r = *reinterpret_cast<TexRowWork*>(smem + sizeof(float) * kTopCorrTex * kTopCorrTex + sizeof(GraphWork<kTopCorrTex>));
     const int tid = threadIdx.x;
     const int n_jobs = *job_count;
+    if (blockIdx.x == 0 && tid == 0 && P.dense_jobs_total) atomicAdd(P.dense_jobs_total, (unsigned long long)n_jobs);
     for (int e = tid; e < kTableN * kTableN; e += kGraphTexThreads) r.table[e] = P.table[e];
     for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
         const size_t pair = (size_t)jobs[jb];

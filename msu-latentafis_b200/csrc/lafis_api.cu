@@ -16,10 +16,9 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/latentafis_b200.h"
+#include "lafis_internal.h"
 #include "compnet.cuh"
 #include "dat_format.h"
-#include "device_common.cuh"
 #include "graph_prune.cuh"
 #include "graph_sparse.cuh"
 #include "minu_big.cuh"
@@ -35,123 +34,13 @@ using namespace lafis;
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;  // elements
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = std::max<size_t>(n, 1);
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-}  // namespace
-
-struct lafis_latents {
-    int n = 0;
-    std::vector<int> status;            // LAFIS_OK / LAFIS_LATENT_EMPTY / LAFIS_ERR_LATENT_LAYOUT
-    std::vector<int> tex_weighted;
-    // host staging, already in device layout
-    int lt_stride = 8;
-    int max_slot_n = 0;
-    std::vector<int> slot_n;            // [3n]
-    std::vector<uint32_t> slot_off;     // [3n] padded offsets
-    uint32_t tot_minu_padded = 0;
-    std::vector<short2> minu_xy;
-    std::vector<float> minu_ori;
-    std::vector<float> minu_desT;
-    std::vector<int> tex_n;             // [n]
-    std::vector<short2> tex_xy;         // [n][lt_stride]
-    std::vector<float> tex_ori;
-    std::vector<float> tex_des;         // [n][lt_stride][96]
-    // one pinned arena holding everything above back to back (single H2D copy)
-    unsigned char* pinned = nullptr;
-    size_t arena_bytes = 0;
-    size_t o_slot_n = 0, o_slot_off = 0, o_minu_xy = 0, o_minu_ori = 0, o_minu_desT = 0, o_tex_n = 0, o_tex_xy = 0,
-           o_tex_ori = 0, o_tex_des = 0, o_weighted = 0, o_status = 0;
-    // device residency
-    lafis_ctx* owner = nullptr;
-    unsigned char* d_arena = nullptr;
-    bool resident = false;
-};
-
-struct lafis_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream_b = nullptr;  // texture chain runs here, concurrently with the minutiae chain on `stream`
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool two_streams = true;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> stage_ev;  // 6 per pipeline chunk + 2 for the tail, grown on demand
-    int stage_chunks = 0;               // chunks of the last match
-    std::string err;
-    int sm_count = 148;
-    size_t work_budget = (size_t)24 << 30;
-
-    float* d_codebook = nullptr;  // [16][256][6]
-    float* d_table = nullptr;     // [50*50]
-    float* d_compnet = nullptr;   // CompNet: k-major weights [46080] + folded BatchNorm scale/shift [4][2][96]
-
-    // gallery
-    DeviceGallery gal;
-    uint32_t index_base = 0;
-    std::vector<std::string> paths;
-    std::vector<int8_t> h_status;
-    std::vector<uint32_t> h_minu_off;  // padded
-    std::vector<uint16_t> h_minu_n;
-    std::vector<uint32_t> h_tex_off;
-    int max_nR = 0, max_nRt = 0;
-    uint64_t algo_bytes = 0;
-
-    // work buffers
-    DevBuf<float> tex_lut, tex_scale;  // fp32 PQ distance tables of the latent batch (K1) + per-row quantiser scales
-    DevBuf<float> rowmax_val;
-    DevBuf<uint16_t> rowmax_j;
-    DevBuf<float> corr_v;
-    DevBuf<uint32_t> corr_ij;
-    DevBuf<int> corr_n;
-    DevBuf<float> sim;            // S matrices of the current chunk
-    DevBuf<int> slow_jobs;        // selection jobs that need the introsort replay
-    int* d_slow_count = nullptr;
-    DevBuf<int> ov_minu, ov_tex;  // overflow job lists of the sparse graph kernels
-    int* d_ov_count = nullptr;    // [2]
-    DevBuf<float> comp;
-    DevBuf<float> final_scores;
-    DevBuf<short4> corr_xy;       // lafis_correspondences: surviving correspondences of the 3 minutiae components
-    DevBuf<int> corr_xy_n;
-    DevBuf<unsigned long long> keys_a, keys_b;
-    DevBuf<HitDev> hits;
-    DevBuf<unsigned char> lat_arena;  // for non-resident latent batches
-    DevBuf<float> compnet_h1;         // CompNet: output of layer1, [n][96]
-    // oversized minutiae pairs (minu_big.cuh): work list and matrices in HBM
-    DevBuf<int> big_jobs, big_slow;
-    DevBuf<unsigned long long> big_soff;
-    DevBuf<float> big_S;
-    DevBuf<uint32_t> big_keys, big_order;
-    int* d_job_counter = nullptr;
-    unsigned long long* d_slow = nullptr;  // [8] counters: 0 minutiae introsort replays, 1 texture top-200 replays,
-                                           //     4..7 texture row-max: queued, exact evaluations, overflowed, templates
-
-    lafis_stats stats{};
-};
-
-namespace {
 
 std::string g_create_error;  // failures before a context exists (lafis_last_error(NULL))
 
+}  // namespace
+
+namespace lafis {
 int fail(lafis_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -162,14 +51,10 @@ int fail(lafis_ctx* c, int code, const char* fmt, ...) {
     else g_create_error = buf;
     return code;
 }
+}  // namespace lafis
 
-#define LAFIS_CUDA(c, expr)                                                                            \
-    do {                                                                                               \
-        cudaError_t e__ = (expr);                                                                      \
-        if (e__ != cudaSuccess)                                                                        \
-            return fail((c), LAFIS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
-                        __FILE__, __LINE__);                                                           \
-    } while (0)
+namespace {
+
 
 void free_gallery(lafis_ctx* c) {
     DeviceGallery& g = c->gal;
@@ -191,6 +76,9 @@ void free_gallery(lafis_ctx* c) {
     c->h_tex_off.clear();
     c->max_nR = c->max_nRt = 0;
     c->algo_bytes = 0;
+    c->gallery_set = false;
+    c->gallery_dir.clear();
+    ++c->gallery_generation;
 }
 
 int create_common(const float* codewords, int device, lafis_ctx** out) {
@@ -318,6 +206,15 @@ void lafis_destroy(lafis_ctx* c) {
     c->hits.release();
     c->lat_arena.release();
     c->compnet_h1.release();
+    c->corr_xy.release();
+    c->corr_xy_n.release();
+    c->enroll_in.release();
+    c->enroll_out.release();
+    c->enroll_pin.release();
+    comm_release(c);
+    c->gathered.release();
+    c->merged.release();
+    c->gather_scores.release();
     c->big_jobs.release();
     c->big_slow.release();
     c->big_soff.release();
@@ -365,6 +262,7 @@ int lafis_gallery_set_packed(lafis_ctx* c, const lafis_packed_gallery* g, uint32
     free_gallery(c);
     const int n = g->n_templates;
     c->index_base = index_base;
+    c->gallery_set = true;  // an empty shard is a gallery too: matches return empty rank lists
     if (n == 0) return LAFIS_OK;
 
     // ---- host plan ----
@@ -756,6 +654,8 @@ int lafis_latents_from_packed(lafis_ctx* c, const lafis_packed_latents* p, lafis
     lafis_latents* L = new lafis_latents();
     L->n = n;
     L->owner = c;
+    L->device = c->device;
+    L->n_minu_templates.assign(p->n_minu_templates, p->n_minu_templates + n);
     L->status.resize(n);
     L->tex_weighted.resize(n);
     L->slot_n.assign(3 * n, 0);
@@ -769,11 +669,14 @@ int lafis_latents_from_packed(lafis_ctx* c, const lafis_packed_latents* p, lafis
         if (nm <= kSelected[0] && nt <= 0) st = LAFIS_LATENT_EMPTY;
         else if (nm + nt < 29) st = LAFIS_ERR_LATENT_LAYOUT;
         L->status[q] = st;
-        L->tex_weighted[q] = (nm == 28 && nt >= 1) ? 1 : 0;
+        // The texture score lands in score[n_minu_templates] (matcher.cpp:414).  The fusion (:188, :293) reads
+        // score[0] + score[1] + score[2] + score[28] * 0.3: with 28 minutiae templates the texture score is the
+        // weighted term (mode 1); with 0, 1 or 2 minutiae templates (and enough texture templates for score[28] to
+        // exist) it sits in one of the three unweighted slots, whose minutiae scores are then all 0 (mode 2).  With
+        // any other template count it is never read, so it is not computed.
+        L->tex_weighted[q] = (nt >= 1 && st == LAFIS_OK) ? (nm == 28 ? 1 : (nm >= 0 && nm <= 2) ? 2 : 0) : 0;
         int ntp = nt > 0 ? (int)(p->tex_off[q + 1] - p->tex_off[q]) : 0;
         if (ntp > kMaxTexture) ntp = kMaxTexture;  // matcher.cpp:544-545
-        // the texture score lands in score[n_minu_templates] (matcher.cpp:414) and only score[28] is
-        // fused (:188): with any other template count it is never read, so it is not computed
         if (!L->tex_weighted[q]) ntp = 0;
         L->tex_n[q] = ntp;
         max_t = std::max(max_t, ntp);
@@ -880,14 +783,16 @@ uint64_t lafis_latents_bytes(const lafis_latents* l) { return l ? (uint64_t)l->a
 int lafis_latents_status(const lafis_latents* l, int q) {
     return (l && q >= 0 && q < l->n) ? l->status[q] : LAFIS_ERR_ARG;
 }
+int lafis_latents_minu_templates(const lafis_latents* l, int q) {
+    return (l && q >= 0 && q < l->n) ? l->n_minu_templates[q] : 0;
+}
 
 void lafis_latents_free(lafis_latents* l) {
     if (!l) return;
-    if (l->owner) cudaSetDevice(l->owner->device);
-    if (l->d_arena) {
-        if (l->owner && l->owner->stream) cudaStreamSynchronize(l->owner->stream);
-        cudaFree(l->d_arena);
-    }
+    // the batch may outlive the context it was created on: only its own device number is used here
+    // (cudaFree waits for outstanding work on that memory)
+    cudaSetDevice(l->device);
+    if (l->d_arena) cudaFree(l->d_arena);
     if (l->pinned) cudaFreeHost(l->pinned);
     delete l;
 }
@@ -900,6 +805,7 @@ int lafis_latents_make_resident(lafis_ctx* c, lafis_latents* l) {
     LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
     l->resident = true;
     l->owner = c;
+    l->device = c->device;
     return LAFIS_OK;
 }
 
@@ -954,8 +860,40 @@ static int run_big_jobs(lafis_ctx* c, cudaStream_t st, MinuBigParams B, const st
     return LAFIS_OK;
 }
 
-static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
+}  // extern "C"
+
+// An empty shard (more ranks than gallery files): empty rank lists, no scores.
+__global__ void fill_empty_hits_kernel(HitDev* hits, size_t n) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        hits[e].score = -CUDART_INF_F;
+        hits[e].index = 0xffffffffu;
+    }
+}
+
+int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     const int Q = L->n, G = c->gal.n;
+    if (G <= 0 && c->gallery_set && Q > 0) {
+        if (topk < 0 || topk > kTopkChunk / 2) return fail(c, LAFIS_ERR_ARG, "topk must be in [0, %d]", kTopkChunk / 2);
+        LAFIS_CUDA(c, cudaSetDevice(c->device));
+        LAFIS_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+        c->stage_chunks = 0;
+        while (c->stage_ev.size() < 2) {
+            cudaEvent_t e;
+            LAFIS_CUDA(c, cudaEventCreate(&e));
+            c->stage_ev.push_back(e);
+        }
+        cudaEventRecord(c->stage_ev[0], c->stream);
+        if (topk > 0) {
+            const size_t nh = (size_t)Q * topk;
+            LAFIS_CUDA(c, c->hits.reserve(nh));
+            fill_empty_hits_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, c->stream>>>(c->hits.p, nh);
+            c->stats.kernel_launches += 1;
+        }
+        cudaEventRecord(c->stage_ev[1], c->stream);
+        LAFIS_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        return LAFIS_OK;
+    }
     if (G <= 0) return fail(c, LAFIS_ERR_NO_GALLERY, "no gallery resident");
     if (Q <= 0) return fail(c, LAFIS_ERR_ARG, "empty latent batch");
     if (topk < 0 || topk > kTopkChunk / 2) return fail(c, LAFIS_ERR_ARG, "topk must be in [0, %d]", kTopkChunk / 2);
@@ -1216,6 +1154,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.n_chunk = n_chunk;
             P.G = G;
             P.comp = c->comp.p;
+            P.dense_jobs_total = c->d_slow + 2;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, sizeof(int), st));
             graph_minu_sparse_kernel<<<grid, SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
@@ -1247,6 +1186,7 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.G = G;
             P.comp = c->comp.p;
             P.slow_path_count = c->d_slow + 1;
+            P.dense_jobs_total = c->d_slow + 3;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk);
             graph_tex_sparse_kernel<<<grid, SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
                 P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
@@ -1310,6 +1250,8 @@ static int run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     c->stats.pairs_scored += (uint64_t)Q * G;
     return LAFIS_OK;
 }
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------------------
 // correspondences of one (latent, gallery template) pair - the reference's save_corr output
@@ -1447,8 +1389,10 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     return LAFIS_OK;
 }
 
+}  // extern "C"
+
 // after the stream has been synchronised: device times of the last match
-static void collect_times(lafis_ctx* c) {
+void lafis::collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&c->stats.last_match_ms, c->ev0, c->ev1);
     float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < c->stage_chunks; ++k)
@@ -1466,12 +1410,16 @@ static void collect_times(lafis_ctx* c) {
     if (cudaMemcpy(cnt, c->d_slow, sizeof cnt, cudaMemcpyDeviceToHost) == cudaSuccess) {
         c->stats.minu_replays = cnt[0];
         c->stats.tex_replays = cnt[1];
+        c->stats.graph_minu_dense_jobs = cnt[2];
+        c->stats.graph_tex_dense_jobs = cnt[3];
         c->stats.tex_queued = cnt[4];
         c->stats.tex_exact = cnt[5];
         c->stats.tex_overflow = cnt[6];
         c->stats.tex_templates = cnt[7];
     }
 }
+
+extern "C" {
 
 int lafis_match_device(lafis_ctx* c, lafis_latents* L, int topk, const void** d_hits, const float** d_all_scores) {
     if (!c || !L) return fail(c, LAFIS_ERR_ARG, "bad argument");
@@ -1544,30 +1492,27 @@ int lafis_pq_encode(lafis_ctx* c, const float* des, int64_t n, uint8_t* codes, i
     LAFIS_CUDA(c, cudaSetDevice(c->device));
     const float* d_des = des;
     uint8_t* d_codes = codes;
-    float* tmp_des = nullptr;
-    uint8_t* tmp_codes = nullptr;
+    const size_t in_bytes = sizeof(float) * kDesLen * (size_t)n, out_bytes = (size_t)n * kSubs;
     if (!on_device) {
-        LAFIS_CUDA(c, cudaMalloc(&tmp_des, sizeof(float) * kDesLen * (size_t)n));
-        if (cudaMalloc(&tmp_codes, (size_t)n * kSubs) != cudaSuccess) {
-            cudaFree(tmp_des);
-            return fail(c, LAFIS_ERR_CUDA, "cudaMalloc failed");
-        }
-        cudaMemcpyAsync(tmp_des, des, sizeof(float) * kDesLen * (size_t)n, cudaMemcpyHostToDevice, c->stream);
-        d_des = tmp_des;
-        d_codes = tmp_codes;
+        // staging buffers owned by the context: they only grow, so a stream of enrollment calls performs no
+        // allocation; the descriptors pass through pinned memory so that the copies are truly asynchronous
+        LAFIS_CUDA(c, c->enroll_in.reserve(in_bytes));
+        LAFIS_CUDA(c, c->enroll_out.reserve(out_bytes));
+        LAFIS_CUDA(c, c->enroll_pin.reserve(in_bytes + out_bytes));
+        std::memcpy(c->enroll_pin.p, des, in_bytes);
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->enroll_in.p, c->enroll_pin.p, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_des = reinterpret_cast<const float*>(c->enroll_in.p);
+        d_codes = c->enroll_out.p;
     }
     const int pts_per_block = 256 / 16;
     pq_encode_kernel<<<(unsigned)((n + pts_per_block - 1) / pts_per_block), 256, 0, c->stream>>>(d_des, (long long)n,
                                                                                                c->d_codebook, d_codes);
     c->stats.kernel_launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && !on_device)
-        e = cudaMemcpyAsync(codes, tmp_codes, (size_t)n * kSubs, cudaMemcpyDeviceToHost, c->stream);
-    cudaError_t e2 = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp_des);
-    cudaFree(tmp_codes);
-    if (e != cudaSuccess || e2 != cudaSuccess)
-        return fail(c, LAFIS_ERR_CUDA, "pq_encode failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    LAFIS_CUDA(c, cudaGetLastError());
+    if (!on_device)
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->enroll_pin.p + in_bytes, d_codes, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!on_device) std::memcpy(codes, c->enroll_pin.p + in_bytes, out_bytes);
     return LAFIS_OK;
 }
 
@@ -1610,18 +1555,16 @@ int lafis_compress_descriptors(lafis_ctx* c, const float* des_in, int64_t n, flo
     LAFIS_CUDA(c, cudaSetDevice(c->device));
     const float* d_in = des_in;
     float* d_out = des_out;
-    float* tmp_in = nullptr;
-    float* tmp_out = nullptr;
+    const size_t in_bytes = sizeof(float) * kCompIn * (size_t)n, out_bytes = sizeof(float) * kCompOut * (size_t)n;
     LAFIS_CUDA(c, c->compnet_h1.reserve((size_t)n * kCompOut));
-    if (!on_device) {
-        LAFIS_CUDA(c, cudaMalloc(&tmp_in, sizeof(float) * kCompIn * (size_t)n));
-        if (cudaMalloc(&tmp_out, sizeof(float) * kCompOut * (size_t)n) != cudaSuccess) {
-            cudaFree(tmp_in);
-            return fail(c, LAFIS_ERR_CUDA, "cudaMalloc failed");
-        }
-        cudaMemcpyAsync(tmp_in, des_in, sizeof(float) * kCompIn * (size_t)n, cudaMemcpyHostToDevice, c->stream);
-        d_in = tmp_in;
-        d_out = tmp_out;
+    if (!on_device) {  // persistent staging, as in lafis_pq_encode
+        LAFIS_CUDA(c, c->enroll_in.reserve(in_bytes));
+        LAFIS_CUDA(c, c->enroll_out.reserve(out_bytes));
+        LAFIS_CUDA(c, c->enroll_pin.reserve(in_bytes + out_bytes));
+        std::memcpy(c->enroll_pin.p, des_in, in_bytes);
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->enroll_in.p, c->enroll_pin.p, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_in = reinterpret_cast<const float*>(c->enroll_in.p);
+        d_out = reinterpret_cast<float*>(c->enroll_out.p);
     }
     CompNetParams P;
     P.x = d_in;
@@ -1637,14 +1580,11 @@ int lafis_compress_descriptors(lafis_ctx* c, const float* des_in, int64_t n, flo
     compnet_l1_kernel<<<grid1, kCompWarpsL1 * 32, compnet_l1_smem_bytes(), c->stream>>>(P);
     compnet_l234_kernel<<<grid2, kCompWarpsL234 * 32, compnet_l234_smem_bytes(), c->stream>>>(P);
     c->stats.kernel_launches += 2;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && !on_device)
-        e = cudaMemcpyAsync(des_out, tmp_out, sizeof(float) * kCompOut * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-    cudaError_t e2 = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp_in);
-    cudaFree(tmp_out);
-    if (e != cudaSuccess || e2 != cudaSuccess)
-        return fail(c, LAFIS_ERR_CUDA, "compress_descriptors failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    LAFIS_CUDA(c, cudaGetLastError());
+    if (!on_device)
+        LAFIS_CUDA(c, cudaMemcpyAsync(c->enroll_pin.p + in_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!on_device) std::memcpy(des_out, c->enroll_pin.p + in_bytes, out_bytes);
     return LAFIS_OK;
 }
 

@@ -1,8 +1,11 @@
 // Drop-in command line of the reference matcher (matching/main.cpp:35-87):
-//   match [-c codebook.dat] [-s scoredir/] [-g gallerydir] (-l latent.dat | -ldir latentdir) [-d device]
+//   match [-c codebook.dat] [-s scoredir/] [-g gallerydir] (-l latent.dat | -ldir latentdir) [-d device] [-gpus N]
 // Flags take precedence over ../afis.config (relative to the working directory).  Unlike the
 // reference the config file is optional when every needed flag is given.
+// -gpus N (or LAFIS_GPUS=N) shards the gallery over devices 0..N-1 of this process (contiguous index ranges,
+// one NCCL all-gather per match, score rows gathered to device 0); the files written are the same, byte for byte.
 #include <algorithm>
+#include <cstdlib>
 #include <filesystem>
 #include <fstream>
 #include <iostream>
@@ -61,11 +64,16 @@ int main(int argc, char** argv) {
     const std::string codebook = args.exists("-c") ? args.get("-c") : config_value(config, "CodebookPath");
     const int device = args.exists("-d") ? std::atoi(args.get("-d").c_str()) : 0;
 
+    int n_gpus = 1;
+    if (args.exists("-gpus")) n_gpus = std::atoi(args.get("-gpus").c_str());
+    else if (const char* e = std::getenv("LAFIS_GPUS")) n_gpus = std::atoi(e);
     lafis_ctx* ctx = nullptr;
-    int rc = lafis_create(codebook.c_str(), device, &ctx);
+    lafis_group* group = nullptr;
+    int rc = n_gpus > 1 ? lafis_group_create(codebook.c_str(), nullptr, n_gpus, &group) : lafis_create(codebook.c_str(), device, &ctx);
     if (rc != LAFIS_OK) {
-        std::cerr << "match: cannot create matcher (status " << rc << "); codebook '" << codebook
-                  << "', CUDA device " << device << " (an sm_100 GPU is required)" << std::endl;
+        std::cerr << "match: cannot create matcher (status " << rc << "): " << lafis_last_error(nullptr) << "; codebook '"
+                  << codebook << "', CUDA device " << device << ", " << n_gpus << " GPU(s) (sm_100 GPUs are required)"
+                  << std::endl;
         return 2;
     }
     std::string score_path;
@@ -83,17 +91,23 @@ int main(int argc, char** argv) {
         gallery_path = config_value(config, "GalleryTemplateDirectory");
     }
     if (args.exists("-l")) {
-        rc = lafis_one2list_matching(ctx, args.get("-l").c_str(), gallery_path.c_str(), score_path.c_str());
+        rc = group ? lafis_group_one2list_matching(group, args.get("-l").c_str(), gallery_path.c_str(), score_path.c_str())
+                   : lafis_one2list_matching(ctx, args.get("-l").c_str(), gallery_path.c_str(), score_path.c_str());
     } else if (args.exists("-ldir")) {
-        rc = lafis_list2list_matching(ctx, args.get("-ldir").c_str(), gallery_path.c_str(), score_path.c_str());
+        rc = group ? lafis_group_list2list_matching(group, args.get("-ldir").c_str(), gallery_path.c_str(), score_path.c_str())
+                   : lafis_list2list_matching(ctx, args.get("-ldir").c_str(), gallery_path.c_str(), score_path.c_str());
     } else {
         std::cout << "Missing argument for latent template or directory. Assuming batch matching, using default "
                      "directory from afis.config"
                   << std::endl;
-        rc = lafis_list2list_matching(ctx, config_value(config, "LatentTemplateDirectory").c_str(), gallery_path.c_str(),
-                                      score_path.c_str());
+        const std::string ldir = config_value(config, "LatentTemplateDirectory");
+        rc = group ? lafis_group_list2list_matching(group, ldir.c_str(), gallery_path.c_str(), score_path.c_str())
+                   : lafis_list2list_matching(ctx, ldir.c_str(), gallery_path.c_str(), score_path.c_str());
     }
-    if (rc < LAFIS_ERR_NO_TEMPLATES) std::cerr << "match: " << lafis_last_error(ctx) << " (status " << rc << ")" << std::endl;
-    lafis_destroy(ctx);
+    if (rc < LAFIS_ERR_NO_TEMPLATES)
+        std::cerr << "match: " << (group ? lafis_group_last_error(group) : lafis_last_error(ctx)) << " (status " << rc << ")"
+                  << std::endl;
+    if (group) lafis_group_destroy(group);
+    else lafis_destroy(ctx);
     return 0;  // matching/main.cpp:86 ignores the drivers' return codes
 }

@@ -18,7 +18,7 @@ namespace lafis {
 struct FuseParams {
     const float* comp;         // [Q][G][4]
     const int* lat_status;     // [Q]
-    const int* tex_weighted;   // [Q]
+    const int* tex_weighted;   // [Q] 0 / 1 (score[28], weight 0.3) / 2 (a slot of score[0..2], weight 1)
     const int8_t* gal_status;  // [G]
     int Q, G;
     float* final_scores;       // [Q][G]
@@ -32,8 +32,11 @@ __global__ void fuse_kernel(FuseParams P) {
     const int8_t gs = P.gal_status[g];
     if (P.lat_status[q] == 0 && (gs == 0 || gs == 2)) {
         const float4 c = *reinterpret_cast<const float4*>(P.comp + e * 4);
-        const float s012 = f_add(f_add(c.x, c.y), c.z);
-        const float s28 = P.tex_weighted[q] ? c.w : 0.0f;
+        const int mode = P.tex_weighted[q];
+        float s0 = c.x;
+        if (mode == 2) s0 = c.w;  // <= 2 minutiae templates: the texture score IS one of score[0..2], the others are 0
+        const float s012 = f_add(f_add(s0, c.y), c.z);
+        const float s28 = mode == 1 ? c.w : 0.0f;
         out = (float)((double)s012 + (double)s28 * 0.3);
     }
     P.final_scores[e] = out;
@@ -56,6 +59,7 @@ __device__ __forceinline__ void rank_unkey(unsigned long long k, float* score, u
 
 constexpr int kTopkThreads = 512;
 constexpr int kTopkChunk = 4096;
+static_assert(kMergeCap == kTopkChunk, "the multi-GPU merge sorts one chunk");
 
 // in-place bitonic sort (descending) of kTopkChunk keys in shared memory
 __device__ __forceinline__ void bitonic_desc(unsigned long long* s) {
@@ -104,11 +108,6 @@ __global__ void __launch_bounds__(kTopkThreads) topk_keys_kernel(const unsigned 
     bitonic_desc(s);
     for (int t = threadIdx.x; t < k; t += kTopkThreads) out[((size_t)q * gridDim.x + chunk) * k + t] = s[t];
 }
-
-struct HitDev {
-    float score;
-    uint32_t index;
-};
 
 __global__ void keys_to_hits_kernel(const unsigned long long* keys, size_t n, HitDev* hits) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -84,7 +84,8 @@ class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_scored", C.c_uint64), ("last_match_ms", C.c_float),
                 ("last_stage_ms", C.c_float * 8), ("minu_replays", C.c_uint64), ("tex_replays", C.c_uint64),
                 ("tex_queued", C.c_uint64), ("tex_exact", C.c_uint64), ("tex_overflow", C.c_uint64),
-                ("tex_templates", C.c_uint64), ("minu_big_jobs", C.c_uint64)]
+                ("tex_templates", C.c_uint64), ("minu_big_jobs", C.c_uint64), ("graph_minu_dense_jobs", C.c_uint64),
+                ("graph_tex_dense_jobs", C.c_uint64)]
 
 
 _lib = None
@@ -98,7 +99,12 @@ EXPORTS = [
     "lafis_correspondences", "lafis_merge_hits", "lafis_merge_hits_device",
     "lafis_one2list_matching", "lafis_list2list_matching", "lafis_forget_gallery_dir", "lafis_pq_encode",
     "lafis_enroll_rolled", "lafis_enroll_latent", "lafis_compnet_load", "lafis_compress_descriptors",
-    "lafis_get_stats", "lafis_set_streams", "lafis_stream",
+    "lafis_get_stats", "lafis_set_streams", "lafis_stream", "lafis_latents_minu_templates",
+    "lafis_comm_unique_id", "lafis_comm_init", "lafis_comm_rank", "lafis_comm_world", "lafis_comm_destroy",
+    "lafis_comm_nccl_version", "lafis_gallery_total", "lafis_match_sharded", "lafis_match_sharded_device",
+    "lafis_group_create", "lafis_group_destroy", "lafis_group_size", "lafis_group_ctx", "lafis_group_last_error",
+    "lafis_group_gallery_load_dir", "lafis_group_gallery_load_files", "lafis_group_gallery_size", "lafis_group_match",
+    "lafis_group_one2list_matching", "lafis_group_list2list_matching",
 ]
 
 
@@ -156,6 +162,30 @@ def load_library():
     L.lafis_set_streams.argtypes = [vp, ci]
     L.lafis_stream.argtypes = [vp]
     L.lafis_stream.restype = vp
+    L.lafis_latents_minu_templates.argtypes = [vp, ci]
+    L.lafis_comm_unique_id.argtypes = [vp]
+    L.lafis_comm_init.argtypes = [vp, vp, ci, ci]
+    L.lafis_comm_rank.argtypes = [vp]
+    L.lafis_comm_world.argtypes = [vp]
+    L.lafis_comm_destroy.argtypes = [vp]
+    L.lafis_comm_destroy.restype = None
+    L.lafis_gallery_total.argtypes = [vp, vp, vp]
+    L.lafis_match_sharded.argtypes = [vp, vp, ci, vp, ci, vp, ci]
+    L.lafis_match_sharded_device.argtypes = [vp, vp, ci, C.POINTER(vp)]
+    L.lafis_group_create.argtypes = [cp, vp, ci, C.POINTER(vp)]
+    L.lafis_group_destroy.argtypes = [vp]
+    L.lafis_group_destroy.restype = None
+    L.lafis_group_size.argtypes = [vp]
+    L.lafis_group_ctx.argtypes = [vp, ci]
+    L.lafis_group_ctx.restype = vp
+    L.lafis_group_last_error.argtypes = [vp]
+    L.lafis_group_last_error.restype = cp
+    L.lafis_group_gallery_load_dir.argtypes = [vp, cp]
+    L.lafis_group_gallery_load_files.argtypes = [vp, C.POINTER(cp), ci]
+    L.lafis_group_gallery_size.argtypes = [vp]
+    L.lafis_group_match.argtypes = [vp, vp, ci, vp, vp]
+    L.lafis_group_one2list_matching.argtypes = [vp, cp, cp, cp]
+    L.lafis_group_list2list_matching.argtypes = [vp, cp, cp, cp]
     _lib = L
     return L
 
@@ -331,9 +361,16 @@ def compnet_layers(state):
 class Matcher:
     """`PQ::Matcher` (matching/matcher.h:34-52) on one B200."""
 
-    def __init__(self, code_file: Optional[str] = None, device: int = 0, codebook: Optional[np.ndarray] = None):
+    def __init__(self, code_file: Optional[str] = None, device: int = 0, codebook: Optional[np.ndarray] = None,
+                 _borrowed_ctx=None):
         self.L = load_library()
         self.ctx = C.c_void_p()
+        self._borrowed = _borrowed_ctx is not None
+        if self._borrowed:  # a context owned by a MatcherGroup
+            self.ctx = C.c_void_p(_borrowed_ctx)
+            self.device = device
+            self._keep = None
+            return
         if codebook is not None:
             cb = np.ascontiguousarray(codebook, np.float32)
             rc = self.L.lafis_create_from_codebook(cb.ctypes.data, cb.shape[0], cb.shape[1], cb.shape[2], device,
@@ -459,6 +496,58 @@ class Matcher:
             raise LafisError(rc, "merge_hits")
         return out
 
+    # ---- multi-GPU: one process per GPU ----
+    def comm_unique_id(self) -> bytes:
+        """Rank 0: the 128-byte id every rank passes to comm_init (ncclGetUniqueId)."""
+        buf = C.create_string_buffer(128)
+        rc = self.L.lafis_comm_unique_id(buf)
+        if rc != LAFIS_OK:
+            raise LafisError(rc, (self.L.lafis_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Collective: joins this context to an NCCL communicator of `world` ranks (ncclCommInitRank)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(self.L.lafis_comm_init(self.ctx, buf, rank, world))
+
+    @property
+    def comm_world(self) -> int:
+        return self.L.lafis_comm_world(self.ctx)
+
+    @property
+    def comm_rank(self) -> int:
+        return self.L.lafis_comm_rank(self.ctx)
+
+    def gallery_total(self):
+        """Collective: (total templates, per-shard bases, per-shard sizes)."""
+        w = self.comm_world
+        base, n = np.zeros(w, np.uint32), np.zeros(w, np.uint32)
+        tot = self.L.lafis_gallery_total(self.ctx, _ptr(base), _ptr(n))
+        if tot < 0:
+            raise LafisError(tot, self.last_error())
+        return tot, base, n
+
+    def match_sharded(self, latents: Latents, topk: int = 0, gather_scores: bool = False, root: int = 0):
+        """Collective over the communicator: this rank's shard is scored, the per-shard rank lists are all-gathered
+        (ncclAllGather) and merged on the device; with gather_scores the score rows of all shards arrive on `root`.
+        -> dict(hits [Q, topk] global lists on every rank, scores [Q, G_total] on root else None)"""
+        Q = latents.n
+        hits = np.zeros((Q, topk), HIT_DTYPE) if topk > 0 else None
+        scores = None
+        if gather_scores:
+            tot = self.gallery_total()[0]
+            if self.comm_rank in (root, -1):
+                scores = np.zeros((Q, tot), np.float32)
+        self._chk(self.L.lafis_match_sharded(self.ctx, latents.h, topk, _ptr(hits), 1 if gather_scores else 0, _ptr(scores),
+                                             root))
+        return {"hits": hits, "scores": scores}
+
+    def match_sharded_device(self, latents: Latents, topk: int) -> int:
+        """Same exchange, the merged global rank lists stay in HBM: returns the raw device pointer."""
+        dh = C.c_void_p()
+        self._chk(self.L.lafis_match_sharded_device(self.ctx, latents.h, topk, C.byref(dh)))
+        return dh.value
+
     def merge_hits_device(self, d_gathered: int, n_latents: int, n_lists: int, topk: int, d_out: int) -> None:
         """[n_lists, Q, topk] gathered rank lists in HBM -> [Q, topk]; enqueued on the matcher's stream."""
         self._chk(self.L.lafis_merge_hits_device(self.ctx, d_gathered, n_latents, n_lists, topk, d_out))
@@ -546,7 +635,8 @@ class Matcher:
                 "last_match_ms": float(s.last_match_ms), "last_stage_ms": [float(x) for x in s.last_stage_ms],
                 "minu_replays": int(s.minu_replays), "tex_replays": int(s.tex_replays), "tex_queued": int(s.tex_queued),
                 "tex_exact": int(s.tex_exact), "tex_overflow": int(s.tex_overflow), "tex_templates": int(s.tex_templates),
-                "minu_big_jobs": int(s.minu_big_jobs)}
+                "minu_big_jobs": int(s.minu_big_jobs), "graph_minu_dense_jobs": int(s.graph_minu_dense_jobs),
+                "graph_tex_dense_jobs": int(s.graph_tex_dense_jobs)}
 
     def set_streams(self, n: int) -> None:
         """2: texture chain on a second stream (default); 1: all kernels serialised on one stream."""
@@ -564,9 +654,79 @@ class Matcher:
             raise LafisError(rc, self.last_error())
 
     def close(self):
-        if self.ctx:
+        if self.ctx and not self._borrowed:
             self.L.lafis_destroy(self.ctx)
-            self.ctx = C.c_void_p()
+        self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MatcherGroup:
+    """`PQ::Matcher` over several B200s of one process: the gallery is sharded over the devices (contiguous index
+    ranges), every match ends in one NCCL all-gather of the shards' rank lists + the device-side merge, and the N-vs-N
+    drivers gather the score rows to device 0.  Same drivers, same files as `Matcher`."""
+
+    def __init__(self, code_file: str, devices: Sequence[int]):
+        self.L = load_library()
+        self.g = C.c_void_p()
+        dev = np.asarray(list(devices), np.int32)
+        rc = self.L.lafis_group_create(os.fsencode(code_file), dev.ctypes.data, len(dev), C.byref(self.g))
+        if rc != LAFIS_OK:
+            self.g = C.c_void_p()
+            raise LafisError(rc, (self.L.lafis_last_error(None) or b"").decode())
+        self.members = [Matcher(device=int(d), _borrowed_ctx=self.L.lafis_group_ctx(self.g, i)) for i, d in enumerate(dev)]
+
+    def __len__(self):
+        return self.L.lafis_group_size(self.g)
+
+    def _chk(self, rc: int):
+        if rc != LAFIS_OK:
+            raise LafisError(rc, (self.L.lafis_group_last_error(self.g) or b"").decode())
+
+    def load_gallery_dir(self, rolled_dir: str) -> int:
+        self._chk(self.L.lafis_group_gallery_load_dir(self.g, os.fsencode(rolled_dir)))
+        return self.gallery_size
+
+    def load_gallery_files(self, paths: Sequence[str]) -> int:
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self._chk(self.L.lafis_group_gallery_load_files(self.g, arr, len(paths)))
+        return self.gallery_size
+
+    @property
+    def gallery_size(self) -> int:
+        return self.L.lafis_group_gallery_size(self.g)
+
+    def load_latents(self, paths: Sequence[str]) -> Latents:
+        return self.members[0].load_latents(paths)
+
+    def latents_from_packed(self, p: PackedLatents) -> Latents:
+        return self.members[0].latents_from_packed(p)
+
+    def match(self, latents: Latents, topk: int = 0, want_scores: bool = True):
+        Q, G = latents.n, self.gallery_size
+        hits = np.zeros((Q, topk), HIT_DTYPE) if topk > 0 else None
+        scores = np.zeros((Q, G), np.float32) if want_scores else None
+        self._chk(self.L.lafis_group_match(self.g, latents.h, topk, _ptr(hits), _ptr(scores)))
+        return {"hits": hits, "scores": scores}
+
+    def One2List_matching(self, latent_template_file: str, rolled_dir: str, score_path: str) -> int:
+        return self.L.lafis_group_one2list_matching(self.g, os.fsencode(latent_template_file), os.fsencode(rolled_dir),
+                                                    os.fsencode(score_path))
+
+    def List2List_matching(self, latent_dir: str, rolled_dir: str, score_path: str) -> int:
+        return self.L.lafis_group_list2list_matching(self.g, os.fsencode(latent_dir), os.fsencode(rolled_dir),
+                                                     os.fsencode(score_path))
+
+    def close(self):
+        if self.g:
+            for m in self.members:
+                m.ctx = C.c_void_p()
+            self.L.lafis_group_destroy(self.g)
+            self.g = C.c_void_p()
 
     def __del__(self):
         try:

@@ -91,6 +91,12 @@ def test_correspondences_match_the_reference_save_corr(pkg, matcher, golden, tmp
         if j not in first or stem in UB_GALLERY:
             continue
         a = first[j]
+        if matcher.gallery_template(j).minu == []:
+            # no minutiae template on the rolled side: the reference never enters the minutiae loop (matcher.cpp:400),
+            # so no correspondence file is created for this print
+            assert not any(os.path.exists(os.path.join(sdir, f"corrlA_{stem}_{s}.csv")) for s in range(3)), stem
+            assert int(corr_n[i, j].sum()) == 0
+            continue
         for s in range(3):
             path = os.path.join(sdir, f"corrlA_{stem}_{s}.csv")
             text = open(path).read()
@@ -98,7 +104,7 @@ def test_correspondences_match_the_reference_save_corr(pkg, matcher, golden, tmp
             assert text == want, (stem, s)
             a += corr_n[i, j, s]
             n_files += 1
-    assert n_files >= 30
+    assert n_files >= 27
 
 
 def test_synthetic_vs_oracle_bit_exact(pkg, matcher, golden, oracle):
