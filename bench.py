@@ -298,10 +298,15 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log (communicator, ranks, transport) goes to stderr: stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's own log (communicator, ranks, transport) must not reach stdout, which carries the one JSON line: it
+        # is written to a per-process file and replayed on stderr once the communicators exist
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        nccl_log = None
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            nccl_log = os.path.join(tempfile.gettempdir(), f"lafis_nccl_{os.getpid()}.log")
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = entry.load_package()
@@ -320,6 +325,12 @@ def run_b200_arm(args):
         comm = {"world": m.comm_world, "rank0": m.comm_rank, "backend": "NCCL (liblatentafis_b200.so: ncclAllGather of rank lists)",
                 "nccl_version": v}
         print(f"[lafis] rank {rank}: NCCL communicator ready, nranks {m.comm_world}, version {v}", file=sys.stderr)
+        if nccl_log and os.path.isfile(nccl_log):
+            with open(nccl_log, errors="replace") as f:
+                for ln in f:
+                    if "nranks" in ln or "Init COMPLETE" in ln or "NCCL version" in ln:
+                        sys.stderr.write(ln)
+            sys.stderr.flush()
     ext = torch.cuda.ExternalStream(m.stream, device=dev)
     G = args.gallery_per_gpu or (100000 if world == 1 else 125000)
     K = args.topk

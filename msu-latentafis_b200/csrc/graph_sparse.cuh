@@ -30,90 +30,80 @@ template <bool LOOKUP>
 struct SparseGeom;
 template <>
 struct SparseGeom<false> {  // minutiae: <= 120 candidates
-    static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 3072;
+    static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 3072, NCH = 4;
 };
 template <>
 struct SparseGeom<true> {  // texture: <= 200 candidates
-    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 5632;
+    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 4608, NCH = 7;
 };
 
+// Working set of one job.  The graph is built symmetrically: only the pairs a < b are tested, a bit matrix M records
+// which of them may be connected (row a gets bit b from the test's ballot, row b gets bit a from a per-lane
+// accumulator flushed with one shared-memory atomic per row chunk); the exact entries are then computed ONCE per
+// surviving pair, the pairs spread evenly over all threads, and stored at both CSR positions, which follow from
+// popcounts of the two bit rows.
 template <bool LOOKUP>
 struct SparseWork {
     using G = SparseGeom<LOOKUP>;
-    float vals[G::CAP];  // CSR values; before the graph is built the texture kernel sorts row maxima here
+    static constexpr int P2 = G::MAXP <= 128 ? 128 : 256;
+    float vals[G::CAP];            // CSR values; before the graph is built the texture kernel sorts row maxima here
+    float4 cf[G::MAXP];            // candidate coordinates as floats (exact): latent x, rolled x, latent y, rolled y
+    uint32_t M[G::MAXP][G::NCH];   // bit matrix of possibly connected pairs
     float v[G::MAXP];
     float lo[G::MAXP], ro[G::MAXP];
-    float b[G::MAXP], c[G::MAXP];
-    short2 lxy[G::MAXP], rxy[G::MAXP];
-    // texture graph only: the same coordinates as floats (exact), its pre-test runs on the fp32 pipes
-    float2 lxyf[LOOKUP ? G::MAXP : 1], rxyf[LOOKUP ? G::MAXP : 1];
     unsigned short li[G::MAXP], rj[G::MAXP];
-    unsigned short row_start[G::MAXP], row_len[G::MAXP];
-    unsigned short y[G::MAXP];    // candidates in std::sort order
-    unsigned short sel[G::MAXP];  // accepted candidates, acceptance order
+    unsigned short row_start[P2], row_len[G::MAXP];
     unsigned char cols[G::CAP];
-    unsigned char rowj[G::NT / 32][G::MAXP];  // per-warp scratch: columns that passed the cheap test
-    unsigned long long skeys[G::MAXP <= 128 ? 128 : 256];  // (b, index) keys of the candidate ranking
+    unsigned short up_pos[P2];     // first CSR slot right of the diagonal of every row
+    union {
+        unsigned short up_start[P2 + 1];   // prefix sums of the rows' counts of pairs a < b: dead once the CSR is built
+        struct {
+            float b[G::MAXP], c[G::MAXP];
+            unsigned short y[G::MAXP];     // candidates in std::sort order
+            unsigned short sel[G::MAXP];   // accepted candidates, acceptance order
+            unsigned long long skeys[P2];  // (b, index) keys of the candidate ranking
+        } it;
+    } u;
+    int wsum[G::NT / 32];
     float f;
-    int overflow, tie, nsel;
+    int overflow, tie, nsel, npairs;
     // orientation stage (<= 32 survivors), only touched when the introsort replay is needed
     float s2[32];
     unsigned short y2[32];
 };
 
-// Cheap, conservative pre-test of "H[a][b] may be non-zero" evaluated for ALL pairs; the exact entry is then
-// computed only for the survivors (~9 % of the pairs of a non-mated print), compacted so that the expensive
-// correctly-rounded square roots and divisions run on full warps.
-// Coordinates arrive as floats (small integers, exact) so that no integer->float conversion and no 64-bit
-// integer product is needed per pair.
+// Cheap, conservative test of "H[a][b] may be non-zero" for all pairs a < b; the exact entry is computed only for the
+// survivors (~9 % of the pairs of a non-mated print).  Coordinates are small integers held exactly in fp32, laid out
+// so that the latent and the rolled difference form one packed pair: two FFMA2, one FMUL2 and one FFMA2 give both
+// squared distances (sm_100 packed fp32: half the issue slots of the scalar form in an issue-bound kernel).
+//   minutiae (matcher.cpp:1372-1384): |d1 - d2| <= 30.04  <=>  (s1 + s2 - 902.4) / 2 <= sqrt(s1 s2), s = d^2 an exact
+//     integer below 2^23 (coordinates below 2048: jobs with larger ones go to the dense kernel); rounding moves the
+//     comparison by < 0.2 squared pixels, the margin over 30^2 is 2.4: nothing with |d1 - d2| <= 30 is rejected.
+//   texture (matcher.cpp:1246-1266, table[dx][dy] = fl(16 sqrt(dx^2 + dy^2))): |d1 - d2| <= 30 needs
+//     (sqrt(s1) - sqrt(s2))^2 <= (30/16)^2 = 3.515625; tested with 3.625 (table entries are rounded to fp32, relative
+//     6e-8 on values <= 1110): never rejects a connected pair.  The |dx|, |dy| < 50 condition of :1257 is left to the
+//     exact entry (pair_h returns 0 then; such a pair's test result is irrelevant).
 template <bool LOOKUP>
-__device__ __forceinline__ bool pair_may_connect(float2 la, float2 lb, float2 ra, float2 rb) {
-    const float dx1 = la.x - lb.x, dx2 = ra.x - rb.x, dy1 = la.y - lb.y, dy2 = ra.y - rb.y;  // exact
-    const float s1 = fmaf(dx1, dx1, dy1 * dy1), s2 = fmaf(dx2, dx2, dy2 * dy2);               // exact integers < 2^24
-    if (LOOKUP) {
-        // matcher.cpp:1246-1266 with table[dx][dy] = fl(16 sqrt(dx^2 + dy^2)): |d1 - d2| <= 30 needs
-        // (sqrt(s1) - sqrt(s2))^2 <= (30/16)^2 = 3.515625, i.e. s1 + s2 - 3.515625 <= 2 sqrt(s1 s2), with s < 5000
-        // once every |dx|, |dy| is below 50 (:1257).  Tested with 3.625 (the table entries are rounded to fp32,
-        // relative 6e-8 on values <= 1110; t*t and 4*s1*s2 round with relative 6e-8 on values whose exact
-        // versions differ by > 1e-5 relative whenever the two constants matter): never rejects a connected pair.
-        // (the |dx|, |dy| < 50 condition of :1257 is left to the exact entry: pair_h returns 0 for such pairs, and on
-        //  the reference's <= 50 x 50 block grids it never fails, so testing it here only costs instructions)
-        const float u = fmaxf(fmaf(s1 + s2, 0.5f, -1.8125f), 0.0f);  // (s1 + s2 - 3.625) / 2, exact
-        return u * u <= s1 * s2;
-    } else {
-        // |d1 - d2| <= 30.04  <=>  s1 + s2 - 30.04^2 <= 2 sqrt(s1 s2), with s = d^2 an exact integer below
-        // 2^23 (coordinates below 2048: jobs with larger ones go to the dense kernel).  Rounding moves the
-        // comparison by < 0.2 squared pixels, the margin over 30^2 is 2.4: nothing with |d1 - d2| <= 30 is
-        // rejected here.
-        const float u = fmaxf(fmaf(s1 + s2, 0.5f, -451.2f), 0.0f);
-        return u * u <= s1 * s2;
-    }
-}
-
-// The minutiae graph keeps its candidates' pixel coordinates as short2 in registers (4 chunks) and forms the
-// squared distances in integers; measured faster there than the float-coordinate form above (14.4 vs 13.9 ms).
-// |d1 - d2| <= 30.04  <=>  (s1 + s2 - 902.4) / 2 <= sqrt(s1 s2); coordinates are below 2048 (larger ones: dense kernel).
-__device__ __forceinline__ bool pair_may_connect_px(short2 la, short2 lb, short2 ra, short2 rb) {
-    const int dx1 = (int)la.x - (int)lb.x, dx2 = (int)ra.x - (int)rb.x;
-    const int dy1 = (int)la.y - (int)lb.y, dy2 = (int)ra.y - (int)rb.y;
-    const float s1 = (float)(dx1 * dx1 + dy1 * dy1), s2 = (float)(dx2 * dx2 + dy2 * dy2);  // exact below 2^23
-    const float u = fmaxf(fmaf(s1 + s2, 0.5f, -451.2f), 0.0f);                              // (s1 + s2 - 902.4) / 2
-    return u * u <= s1 * s2;
+__device__ __forceinline__ bool pair_may_connect(float4 a, float4 b) {
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    const float2 p = __ffma2_rn(make_float2(b.x, b.y), m1, make_float2(a.x, a.y));  // (dx1, dx2), exact
+    const float2 q = __ffma2_rn(make_float2(b.z, b.w), m1, make_float2(a.z, a.w));  // (dy1, dy2), exact
+    const float2 s = __ffma2_rn(q, q, __fmul2_rn(p, p));                            // (s1, s2), exact integers
+    const float u = fmaxf(fmaf(s.x + s.y, 0.5f, LOOKUP ? -1.8125f : -451.2f), 0.0f);
+    return u * u <= s.x * s.y;
 }
 
 // H entry of the distance-consistency graph for candidates a, b (symmetric in a, b), exact.
 template <bool LOOKUP>
-__device__ __forceinline__ float pair_h(short2 la, short2 lb, short2 ra, short2 rb, const float* __restrict__ table) {
+__device__ __forceinline__ float pair_h(float4 a, float4 b, const float* __restrict__ table) {
+    const float dx1 = a.x - b.x, dx2 = a.y - b.y, dy1 = a.z - b.z, dy2 = a.w - b.w;  // exact (small integers)
     float d1, d2;
     if (LOOKUP) {  // matcher.cpp:1246-1262
-        const int dx1 = abs((int)la.x - (int)lb.x), dx2 = abs((int)ra.x - (int)rb.x);
-        const int dy1 = abs((int)la.y - (int)lb.y), dy2 = abs((int)ra.y - (int)rb.y);
-        if ((dx1 >= kTableN) | (dx2 >= kTableN) | (dy1 >= kTableN) | (dy2 >= kTableN)) return 0.0f;
-        d1 = __ldg(table + dx1 * kTableN + dy1);
-        d2 = __ldg(table + dx2 * kTableN + dy2);
+        const int ix1 = (int)fabsf(dx1), ix2 = (int)fabsf(dx2), iy1 = (int)fabsf(dy1), iy2 = (int)fabsf(dy2);
+        if ((ix1 >= kTableN) | (ix2 >= kTableN) | (iy1 >= kTableN) | (iy2 >= kTableN)) return 0.0f;
+        d1 = __ldg(table + ix1 * kTableN + iy1);
+        d2 = __ldg(table + ix2 * kTableN + iy2);
     } else {  // matcher.cpp:1372-1384
-        const float dx1 = (float)((int)la.x - (int)lb.x), dx2 = (float)((int)ra.x - (int)rb.x);
-        const float dy1 = (float)((int)la.y - (int)lb.y), dy2 = (float)((int)ra.y - (int)rb.y);
         d1 = __fsqrt_rn(f_add(f_mul(dx1, dx1), f_mul(dy1, dy1)));
         d2 = __fsqrt_rn(f_add(f_mul(dx2, dx2), f_mul(dy2, dy2)));
     }
@@ -126,15 +116,29 @@ __device__ __forceinline__ float pair_h(short2 la, short2 lb, short2 ra, short2 
     return h;
 }
 
-// orientation compatibility of survivors i < j (matcher.cpp:1495-1549); "1" is i, "2" is j
-__device__ __forceinline__ bool angle_compatible(short2 l1, short2 l2, short2 r1, short2 r2, float lo1, float lo2,
-                                                 float ro1, float ro2) {
+// number of set bits of a bit row strictly below column x
+template <int NCH>
+__device__ __forceinline__ int bits_below(const uint32_t* __restrict__ row, int x) {
+    const int wx = x >> 5;
+    const uint32_t low = (1u << (x & 31)) - 1u;
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < NCH; ++w) {
+        const uint32_t word = row[w];
+        n += __popc(w < wx ? word : (w == wx ? (word & low) : 0u));
+    }
+    return n;
+}
+
+// orientation compatibility of survivors i < j (matcher.cpp:1495-1549); "1" is i, "2" is j; coordinates as the
+// exact floats of SparseWork::cf (latent x, rolled x, latent y, rolled y)
+__device__ __forceinline__ bool angle_compatible(float4 c1, float4 c2, float lo1, float lo2, float ro1, float ro2) {
     float a1 = adjust_angle_ref(f_sub(lo1, lo2));
     float a2 = adjust_angle_ref(f_sub(ro1, ro2));
     if ((double)angle_gap_ref(a1, a2) > LAFIS_PI_D / 4.) return false;
-    const float dx1 = (float)((int)l1.x - (int)l2.x), dy1 = (float)((int)l1.y - (int)l2.y);
+    const float dx1 = c1.x - c2.x, dy1 = c1.z - c2.z;  // exact: the reference's int difference converted to float
     const float line1 = -atan2f_fdlibm(dy1, dx1);
-    const float dx2 = (float)((int)r1.x - (int)r2.x), dy2 = (float)((int)r1.y - (int)r2.y);
+    const float dx2 = c1.y - c2.y, dy2 = c1.w - c2.w;
     const float line2 = -atan2f_fdlibm(dy2, dx2);
     a1 = adjust_angle_ref(f_sub(lo1, line1));
     a2 = adjust_angle_ref(f_sub(ro1, line2));
@@ -150,131 +154,190 @@ __device__ __forceinline__ bool angle_compatible(short2 l1, short2 l2, short2 r1
 template <bool LOOKUP>
 __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __restrict__ table, float* score_out) {
     using G = SparseGeom<LOOKUP>;
-    constexpr int NT = G::NT, NW = NT / 32, CAPW = G::CAP / NW, CH = G::MAXP / 32;
+    constexpr int NT = G::NT, NW = NT / 32, CH = G::MAXP / 32, P2 = SparseWork<LOOKUP>::P2;
     constexpr int ITERS = LOOKUP ? 3 : 5;  // matcher.cpp:1284 / :1406
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     *score_out = 0.0f;
     if (num <= 0) return true;
 
-    // ---- CSR rows of the distance-consistency graph ----
+    // ---- bit matrix of possibly connected pairs: only a < b is tested (rows a = warp, warp + NW, ...) ----
     {
-        // column coordinates of the pre-test: registers for the minutiae graph (4 chunks), shared memory for the
-        // texture graph (7 chunks would cost 28 registers and an occupancy step)
-        constexpr int CHR = LOOKUP ? 1 : CH;
-        short2 clxy[CHR], crxy[CHR];
+        constexpr int NCH = G::NCH;
+        // column coordinates: registers for the minutiae graph (4 chunks), shared memory for the texture graph
+        // (7 chunks would cost 28 registers and an occupancy step)
+        float4 colreg[LOOKUP ? 1 : NCH];
         if (!LOOKUP) {
 #pragma unroll
-            for (int c = 0; c < CHR; ++c) {
-                const int j = lane + 32 * c;
-                clxy[c] = (j < num) ? w.lxy[j] : make_short2(0, 0);
-                crxy[c] = (j < num) ? w.rxy[j] : make_short2(0, 0);
-            }
+            for (int c = 0; c < NCH; ++c) colreg[c] = w.cf[lane + 32 * c];
         }
-        const int wbase = warp * CAPW;
-        int used = 0;
-        bool over = false;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        unsigned char* rowj = w.rowj[warp];
-        for (int i = warp; i < num; i += NW) {
-            const short2 la = w.lxy[i], ra = w.rxy[i];
-            // pass 1: columns that may connect to row i, ascending
-            int cnt = 0;
-            if constexpr (LOOKUP) {
-                const float2 laf = w.lxyf[i], raf = w.rxyf[i];
-                for (int j = lane; j - lane < num; j += 32) {
-                    const bool pass = j < num && j != i && pair_may_connect<LOOKUP>(laf, w.lxyf[j], raf, w.rxyf[j]);
-                    const unsigned m = __ballot_sync(0xffffffffu, pass);
-                    if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
-                    cnt += __popc(m);
-                }
-            } else {
+        bool valid[NCH];
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int j = lane + 32 * c;
-                    const bool pass = j < num && j != i && pair_may_connect_px(la, clxy[c], ra, crxy[c]);
+        for (int c = 0; c < NCH; ++c) valid[c] = lane + 32 * c < num;
+        // one phase per row chunk r, so that the column chunks c >= r it meets are known at compile time
+#pragma unroll
+        for (int r = 0; r < NCH; ++r) {
+            if (32 * r >= num) break;  // uniform
+            uint32_t tacc[NCH];  // bit k of tacc[c]: row 32 r + k may connect to my column of chunk c (the transposed bits)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tacc[c] = 0u;
+            const int i_end = min(num, 32 * r + 32);
+            for (int i = 32 * r + warp; i < i_end; i += NW) {
+                const uint32_t kbit = 1u << (i & 31);
+                const float4 row = w.cf[i];
+                uint32_t keep = 0u;
+#pragma unroll
+                for (int c = r; c < NCH; ++c) {
+                    const float4 col = LOOKUP ? w.cf[lane + 32 * c] : colreg[LOOKUP ? 0 : c];
+                    const bool pass = pair_may_connect<LOOKUP>(row, col) & valid[c];
                     const unsigned m = __ballot_sync(0xffffffffu, pass);
-                    if (pass) rowj[cnt + __popc(m & lt_mask)] = (unsigned char)j;
-                    cnt += __popc(m);
+                    if (c > r && pass) tacc[c] |= kbit;
+                    if (lane == c) keep = m;
                 }
+                if (lane == r) keep &= ~kbit;                      // not with itself
+                if (lane >= r && lane < NCH) w.M[i][lane] = keep;  // the row's own chunk and everything right of it
             }
-            __syncwarp();
-            // pass 2: exact entries of the survivors, compacted again (an exact entry can still be 0)
-            int len = 0;
-            for (int b0 = 0; b0 < cnt; b0 += 32) {
-                const int idx = b0 + lane;
-                float h = 0.0f;
-                int j = 0;
-                if (idx < cnt) {
-                    j = rowj[idx];
-                    h = pair_h<LOOKUP>(la, w.lxy[j], ra, w.rxy[j], table);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, h > 0.0f);
-                const int pos = used + len + __popc(m & lt_mask);
-                if (h > 0.0f && pos < CAPW) {
-                    w.vals[wbase + pos] = h;
-                    w.cols[wbase + pos] = (unsigned char)j;
-                }
-                len += __popc(m);
-            }
-            __syncwarp();
-            if (used + len > CAPW) over = true;
-            if (lane == 0) {
-                w.row_start[i] = (unsigned short)(wbase + used);
-                w.row_len[i] = (unsigned short)len;
-            }
-            used += len;
+#pragma unroll
+            for (int c = r + 1; c < NCH; ++c)
+                if (tacc[c]) atomicOr(&w.M[32 * c + lane][r], tacc[c]);
         }
-        if (over && lane == 0) w.overflow = 1;
     }
-    if (tid < num) w.b[tid] = w.v[tid];
+    __syncthreads();
+    // ---- CSR row extents from the bit rows; `up` counts the entries right of the diagonal (pairs a < b) ----
+    {
+        int len = 0, up = 0;
+        if (tid < num) {
+            const int r = tid >> 5, k = tid & 31;
+            const uint32_t above = (k == 31) ? 0u : ~((2u << k) - 1u);
+#pragma unroll
+            for (int c = 0; c < G::NCH; ++c) {
+                const uint32_t word = w.M[tid][c];
+                len += __popc(word);
+                up += __popc(c > r ? word : (c == r ? (word & above) : 0u));
+            }
+        }
+        const int mine = len | (up << 16);
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) w.wsum[warp] = inc;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) before += (k < warp) ? w.wsum[k] : 0;
+        const int excl = before + inc - mine;
+        if (tid < P2) {
+            w.row_start[tid] = (unsigned short)(excl & 0xffff);
+            w.up_pos[tid] = (unsigned short)((excl & 0xffff) + len - up);  // first CSR slot right of the diagonal
+            if (tid < num) w.row_len[tid] = (unsigned short)len;
+            w.u.up_start[tid] = tid < num ? (unsigned short)(excl >> 16) : (unsigned short)0xffffu;
+        }
+        if (tid == NT - 1) {
+            w.npairs = (before + inc) >> 16;
+            if (((before + inc) & 0xffff) > G::CAP) w.overflow = 1;
+        }
+    }
     __syncthreads();
     if (w.overflow) return false;
+    // ---- exact entries, once per pair a < b, stored at both positions.  Pair e of the flat enumeration is found by a
+    //      binary search over the rows' `up` prefix sums and a bit select inside the row; its two CSR slots follow from
+    //      popcounts.  (An exact entry can still be 0: a zero entry adds +0 to the fp32 accumulators below and fails the
+    //      >= 1e-5 test of the greedy pass, like an absent one.) ----
+    {
+        const int np = w.npairs;
+        for (int e = tid; e < np; e += NT) {
+            int a = 0;
+#pragma unroll
+            for (int step = P2 / 2; step >= 1; step >>= 1)
+                if (w.u.up_start[a + step] <= e) a += step;
+            const int k0 = e - w.u.up_start[a];
+            const int r = a >> 5, ka = a & 31;
+            const uint32_t above = (ka == 31) ? 0u : ~((2u << ka) - 1u);
+            int k = k0, cw = 0;
+            uint32_t word = 0u;
+            bool found = false;
+#pragma unroll
+            for (int c = 0; c < G::NCH; ++c) {
+                const uint32_t x0 = w.M[a][c];
+                const uint32_t x = c > r ? x0 : (c == r ? (x0 & above) : 0u);
+                const int cnt = __popc(x);
+                const bool here = !found & (k < cnt);
+                if (here) {
+                    word = x;
+                    cw = c;
+                }
+                found |= here;
+                if (!found) k -= cnt;
+            }
+            int pos = 0;  // position of the k-th set bit of `word`
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) {
+                const int cnt = __popc((word >> pos) & ((1u << sh) - 1u));
+                if (k >= cnt) {
+                    k -= cnt;
+                    pos += sh;
+                }
+            }
+            const int b = 32 * cw + pos;
+            const float h = pair_h<LOOKUP>(w.cf[a], w.cf[b], table);
+            const int pa = w.up_pos[a] + k0;
+            const int pb = w.row_start[b] + bits_below<G::NCH>(w.M[b], a);
+            w.vals[pa] = h;
+            w.cols[pa] = (unsigned char)b;
+            w.vals[pb] = h;
+            w.cols[pb] = (unsigned char)a;
+        }
+    }
+    __syncthreads();  // the prefix sums are dead: their storage becomes the iteration vectors
+    if (tid < num) w.u.it.b[tid] = w.v[tid];
+    __syncthreads();
 
     // ---- power iteration: c = H b (non-zeros, ascending k), b = c * (float)(1 / (sum c + 1e-5)) ----
     for (int it = 0; it < ITERS; ++it) {
         if (tid < num) {
             const int rs = w.row_start[tid], len = w.row_len[tid];
             float acc = 0.0f;
-            for (int e = 0; e < len; ++e) acc = f_add(acc, f_mul(w.vals[rs + e], w.b[w.cols[rs + e]]));
-            w.c[tid] = acc;
+            for (int e = 0; e < len; ++e) acc = f_add(acc, f_mul(w.vals[rs + e], w.u.it.b[w.cols[rs + e]]));
+            w.u.it.c[tid] = acc;
         }
         __syncthreads();
         if (tid == 0) {
-            float sum = w.c[0];
+            float sum = w.u.it.c[0];
 #pragma unroll 8
-            for (int i = 1; i < num; ++i) sum = f_add(sum, w.c[i]);
+            for (int i = 1; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
             w.f = (float)(1.0 / ((double)sum + 0.00001));
         }
         __syncthreads();
-        if (tid < num) w.b[tid] = f_mul(w.c[tid], w.f);
+        if (tid < num) w.u.it.b[tid] = f_mul(w.u.it.c[tid], w.f);
         __syncthreads();
     }
 
     // ---- order by b descending with std::sort's permutation: (value desc, index asc) keys through the block's
     //      bitonic sort; equal values that the greedy pass can reach need the introsort replay ----
     {
-        constexpr int P2 = G::MAXP <= 128 ? 128 : 256;
         static_assert(P2 <= NT && G::MAXN <= P2, "one key per thread");
         unsigned long long k = 0ull;  // padding keys sort last
         if (tid < num) {
-            uint32_t u = __float_as_uint(w.b[tid]);  // b >= 0: the bit pattern orders like the value
+            uint32_t u = __float_as_uint(w.u.it.b[tid]);  // b >= 0: the bit pattern orders like the value
             if (u == 0x80000000u) u = 0u;
             k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffu - (unsigned)tid);
         }
-        if (tid < P2) w.skeys[tid] = k;
+        if (tid < P2) w.u.it.skeys[tid] = k;
         __syncthreads();
-        block_bitonic_desc<NT, 1>(w.skeys, P2);
+        block_bitonic_desc<NT, 1>(w.u.it.skeys, P2);
         if (tid < num) {
-            const unsigned long long me = w.skeys[tid];
-            w.y[tid] = (unsigned short)(0xffffu - (unsigned)(me & 0xffffu));
-            if (tid + 1 < num && num > 16 && (me >> 32) == (w.skeys[tid + 1] >> 32) &&
+            const unsigned long long me = w.u.it.skeys[tid];
+            w.u.it.y[tid] = (unsigned short)(0xffffu - (unsigned)(me & 0xffffu));
+            if (tid + 1 < num && num > 16 && (me >> 32) == (w.u.it.skeys[tid + 1] >> 32) &&
                 !((double)__uint_as_float((uint32_t)(me >> 32)) < 0.0001))
                 w.tie = 1;
         }
     }
     __syncthreads();
     if (w.tie) {
-        if (tid == 0) std_sort_desc_emulate<float, unsigned short>(w.b, w.y, num);
+        if (tid == 0) std_sort_desc_emulate<float, unsigned short>(w.u.it.b, w.u.it.y, num);
         __syncthreads();
     }
     if (warp != 0) return true;  // the rest runs in warp 0 only; thread 0 carries the result
@@ -287,8 +350,8 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int p = lane + 32 * c;
-            ind[c] = (p < num) ? w.y[p] : 0;
-            if (p < num && !((double)w.b[ind[c]] < 0.0001)) open |= 1u << c;
+            ind[c] = (p < num) ? w.u.it.y[p] : 0;
+            if (p < num && !((double)w.u.it.b[ind[c]] < 0.0001)) open |= 1u << c;
         }
         for (;;) {
             int pos = -1;
@@ -298,8 +361,8 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
                 if (m && pos < 0) pos = 32 * c + __ffs(m) - 1;
             }
             if (pos < 0) break;
-            const int s = w.y[pos];
-            if (lane == 0) w.sel[n2] = (unsigned short)s;
+            const int s = w.u.it.y[pos];
+            if (lane == 0) w.u.it.sel[n2] = (unsigned short)s;
             ++n2;
             const unsigned short sli = w.li[s], srj = w.rj[s];
 #pragma unroll
@@ -328,16 +391,16 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
     if (n2 == 0) return true;
 
     // ---- orientation-consistency graph on the n2 survivors, lane = survivor (acceptance order) ----
-    const int me = (lane < n2) ? w.sel[lane] : w.sel[0];
-    const short2 mlxy = w.lxy[me], mrxy = w.rxy[me];
+    const int me = (lane < n2) ? w.u.it.sel[lane] : w.u.it.sel[0];
+    const float4 mcf = w.cf[me];
     const float mlo = w.lo[me], mro = w.ro[me], mv = w.v[me];
     const unsigned short mli = w.li[me], mrj = w.rj[me];
     unsigned mask = 0;
     for (int j = 1; j < n2; ++j) {
-        const short2 olxy = make_short2((short)__shfl_sync(0xffffffffu, (int)mlxy.x, j), (short)__shfl_sync(0xffffffffu, (int)mlxy.y, j));
-        const short2 orxy = make_short2((short)__shfl_sync(0xffffffffu, (int)mrxy.x, j), (short)__shfl_sync(0xffffffffu, (int)mrxy.y, j));
+        const float4 ocf = make_float4(__shfl_sync(0xffffffffu, mcf.x, j), __shfl_sync(0xffffffffu, mcf.y, j),
+                                       __shfl_sync(0xffffffffu, mcf.z, j), __shfl_sync(0xffffffffu, mcf.w, j));
         const float olo = __shfl_sync(0xffffffffu, mlo, j), oro = __shfl_sync(0xffffffffu, mro, j);
-        if (lane < j && angle_compatible(mlxy, olxy, mrxy, orxy, mlo, olo, mro, oro)) mask |= 1u << j;
+        if (lane < j && angle_compatible(mcf, ocf, mlo, olo, mro, oro)) mask |= 1u << j;
     }
     for (int j = 0; j < n2; ++j) {  // symmetric half
         const unsigned mj = __shfl_sync(0xffffffffu, mask, j);
@@ -416,7 +479,9 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
     if (tid == 0) {
         w.overflow = 0;
         w.tie = 0;
+        w.npairs = 0;
     }
+    for (int e = tid; e < SparseGeom<false>::MAXP * SparseGeom<false>::NCH; e += SparseGeom<false>::NT) (&w.M[0][0])[e] = 0u;
     int big = 0;
     if (tid < num) {
         const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
@@ -425,14 +490,15 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         w.li[tid] = (unsigned short)i;
         w.rj[tid] = (unsigned short)j;
         const uint32_t lo = P.slot_off[q * 3 + slot] + i, go = P.minu_off[P.g0 + tl] + j;
-        w.lxy[tid] = P.lat_xy[lo];
-        w.rxy[tid] = P.gal_xy[go];
+        const short2 lxy = P.lat_xy[lo], rxy = P.gal_xy[go];
+        w.cf[tid] = make_float4((float)lxy.x, (float)rxy.x, (float)lxy.y, (float)rxy.y);
         w.lo[tid] = P.lat_ori[lo];
         w.ro[tid] = P.gal_ori[go];
         // the pre-test squares coordinate differences in fp32: exact only below 2048 px
         // (coordinates in [0, 2048): differences below 2048, squared distances below 2^23)
-        big = ((unsigned)(int)w.lxy[tid].x | (unsigned)(int)w.lxy[tid].y | (unsigned)(int)w.rxy[tid].x |
-               (unsigned)(int)w.rxy[tid].y) >= 2048u;
+        big = ((unsigned)(int)lxy.x | (unsigned)(int)lxy.y | (unsigned)(int)rxy.x | (unsigned)(int)rxy.y) >= 2048u;
+    } else if (tid < SparseGeom<false>::MAXP) {
+        w.cf[tid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (__syncthreads_or(big)) {  // larger images: the dense kernel evaluates every entry exactly
         if (tid == 0) ov.jobs[atomicAdd(ov.count, 1)] = (int)oidx;
@@ -475,7 +541,9 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
     if (tid == 0) {
         w.overflow = 0;
         w.tie = 0;
+        w.npairs = 0;
     }
+    for (int e = tid; e < SparseGeom<true>::MAXP * SparseGeom<true>::NCH; e += NT) (&w.M[0][0])[e] = 0u;
     const size_t rbase = pair * (size_t)P.lt_stride;
     int num;
     if (nLt > kTopCorrTex) {
@@ -534,12 +602,12 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
     __syncthreads();  // the key area becomes the CSR value area from here on
     if (tid < num) {
         const int i = w.li[tid], j = w.rj[tid];
-        w.lxy[tid] = P.lat_xy[(size_t)q * P.lt_stride + i];
-        w.rxy[tid] = P.gal_xy[gbase + j];
-        w.lxyf[tid] = make_float2((float)w.lxy[tid].x, (float)w.lxy[tid].y);
-        w.rxyf[tid] = make_float2((float)w.rxy[tid].x, (float)w.rxy[tid].y);
+        const short2 lxy = P.lat_xy[(size_t)q * P.lt_stride + i], rxy = P.gal_xy[gbase + j];
+        w.cf[tid] = make_float4((float)lxy.x, (float)rxy.x, (float)lxy.y, (float)rxy.y);
         w.lo[tid] = P.lat_ori[(size_t)q * P.lt_stride + i];
         w.ro[tid] = P.gal_ori[gbase + j];
+    } else if (tid < SparseGeom<true>::MAXP) {
+        w.cf[tid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncthreads();
     float score;
