@@ -82,6 +82,7 @@ __device__ __forceinline__ void block_bitonic_desc(unsigned long long* skey, int
 #pragma unroll
         for (int e = 0; e < KPT; ++e) {
             const int i = tid + e * NT;
+            if ((i & ~31) >= np2) continue;  // warp-uniform: this warp holds no key of slot e
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine[e], j);
             const bool take_max = ((i & j) == 0) == ((i & k) == 0);
             mine[e] = ((mine[e] > other) == take_max) ? mine[e] : other;

@@ -5,12 +5,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <limits>
 #include <string>
 #include <thread>
@@ -56,6 +58,19 @@ int fail(lafis_ctx* c, int code, const char* fmt, ...) {
 namespace {
 
 
+// Work buffers of a pipeline chunk: as much as the device can spare once the gallery is resident (the similarity
+// matrices alone are ~146 KB per (latent, template) pair, so a 256-latent batch wants tens of GB to keep its chunks above
+// a few thousand templates).  Sized when the gallery changes, not per match: cudaMemGetInfo takes a driver lock that
+// monitoring tools (nvidia-smi polling) hold for milliseconds at a time.
+void size_work_budget(lafis_ctx* c) {
+    if (c->work_budget_fixed) return;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+    const size_t held = sizeof(float) * (c->sim.cap + c->rowmax_val.cap + c->corr_v.cap) + 2 * c->rowmax_j.cap +
+                        4 * (c->corr_ij.cap + c->corr_n.cap + c->slow_jobs.cap + c->ov_minu.cap + c->ov_tex.cap);
+    c->work_budget = std::min<size_t>(std::max<size_t>((free_b + held) / 2, (size_t)1 << 30), (size_t)64 << 30);
+}
+
 void free_gallery(lafis_ctx* c) {
     DeviceGallery& g = c->gal;
     cudaFree(g.minu_off);
@@ -94,7 +109,11 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     lafis_ctx* c = new lafis_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* s = getenv("LAFIS_WORK_BYTES")) c->work_budget = (size_t)strtoull(s, nullptr, 10);
+    c->work_budget_fixed = false;
+    if (const char* s = getenv("LAFIS_WORK_BYTES")) {
+        c->work_budget = (size_t)strtoull(s, nullptr, 10);
+        c->work_budget_fixed = true;
+    }
     cudaError_t last = cudaSuccess;
     const char* what = "";
 #define TRY(expr) (ok = ok && ((last = (expr)) == cudaSuccess || (what = #expr, false)))
@@ -397,6 +416,7 @@ int lafis_gallery_set_packed(lafis_ctx* c, const lafis_packed_gallery* g, uint32
     c->max_nRt = max_nRt;
     c->algo_bytes = algo;
     c->paths.assign(n, std::string());
+    size_work_budget(c);
     return LAFIS_OK;
 }
 
@@ -406,137 +426,222 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
     if (n == 0) return fail(c, LAFIS_ERR_NO_TEMPLATES, "no rolled templates");
     const long long lo = (long long)n * shard_rank / shard_count, hi = (long long)n * (shard_rank + 1) / shard_count;
     const int m = (int)(hi - lo);
-    // Parse with all host cores: every thread reads a contiguous range of files into its own packed part
-    // (the reference re-parses every rolled file for every latent, matcher.cpp:173/:278; here it happens once),
-    // then every thread uploads its part to its place in the device staging arrays.
-    struct Part {
-        std::vector<uint32_t> n_minu, n_tex;  // per template
-        std::vector<int16_t> mx, my, tx, ty;
-        std::vector<float> mori, mdes, tori;
-        std::vector<uint8_t> codes;
+    // The reference re-parses every rolled file for every latent (matcher.cpp:173/:278); here every file is parsed once,
+    // by all host cores.  Each parser thread owns a contiguous range of files and a ring of pinned staging buffers: it
+    // packs the templates it has parsed into the current buffer and, when that is full, reserves a region of ONE device
+    // pool and ships the buffer there with an asynchronous copy on its own stream while it goes on parsing into the next
+    // buffer.  No pageable copy, no consolidated host copy of the gallery, and the upload overlaps the parsing.
+    LAFIS_CUDA(c, cudaSetDevice(c->device));
+    LAFIS_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_gallery(c);
+    c->index_base = (uint32_t)lo;
+    c->gallery_set = true;
+    if (m == 0) return LAFIS_OK;  // an empty shard (more ranks than files)
+
+    const bool timing = getenv("LAFIS_INGEST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(now() - t).count();
     };
+    const auto t_all = now();
     const int n_threads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 64, m / 32 + 1}));
-    std::vector<Part> parts(n_threads);
-    std::vector<int8_t> status(m);
-    std::vector<std::string> kept(m);
     auto range_lo = [&](int i) { return (int)((long long)m * i / n_threads); };
-    auto parse = [&](int i) {
-        Part& P = parts[i];
-        for (int t = range_lo(i); t < range_lo(i + 1); ++t) {
-            RolledTemplate R;
-            read_rolled_dat(paths[lo + t], R);
-            kept[t] = paths[lo + t];
-            status[t] = (int8_t)R.status;
-            P.mx.insert(P.mx.end(), R.minu.x.begin(), R.minu.x.end());
-            P.my.insert(P.my.end(), R.minu.y.begin(), R.minu.y.end());
-            P.mori.insert(P.mori.end(), R.minu.ori.begin(), R.minu.ori.end());
-            P.mdes.insert(P.mdes.end(), R.minu.des.begin(), R.minu.des.end());
-            P.tx.insert(P.tx.end(), R.tex.x.begin(), R.tex.x.end());
-            P.ty.insert(P.ty.end(), R.tex.y.begin(), R.tex.y.end());
-            P.tori.insert(P.tori.end(), R.tex.ori.begin(), R.tex.ori.end());
-            P.codes.insert(P.codes.end(), R.tex.codes.begin(), R.tex.codes.end());
-            P.n_minu.push_back((uint32_t)R.minu.x.size());
-            P.n_tex.push_back((uint32_t)R.tex.x.size());
-        }
-    };
     auto run_parallel = [&](auto&& fn) {
         std::vector<std::thread> pool;
         for (int i = 1; i < n_threads; ++i) pool.emplace_back(fn, i);
         fn(0);
         for (std::thread& th : pool) th.join();
     };
-    const bool timing = getenv("LAFIS_INGEST_TIMING") != nullptr;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
-        return std::chrono::duration<double, std::milli>(now() - t).count();
-    };
-    const auto t_parse = now();
-    run_parallel(parse);
-    const double parse_ms = ms_since(t_parse);
-    const auto t_up = now();
-    std::vector<uint32_t> minu_off(m + 1, 0), tex_off(m + 1, 0);
-    std::vector<size_t> part_m(n_threads + 1, 0), part_t(n_threads + 1, 0);
-    for (int i = 0; i < n_threads; ++i) {
-        part_m[i + 1] = part_m[i] + parts[i].mx.size();
-        part_t[i + 1] = part_t[i] + parts[i].tx.size();
-        int t = range_lo(i);
-        for (size_t k = 0; k < parts[i].n_minu.size(); ++k, ++t) {
-            minu_off[t + 1] = minu_off[t] + parts[i].n_minu[k];
-            tex_off[t + 1] = tex_off[t] + parts[i].n_tex[k];
-        }
-    }
-    const size_t tot_m = part_m[n_threads], tot_t = part_t[n_threads];
-    if (tot_m > 0xffffffffull / 2 || tot_t > 0xffffffffull / 2) return fail(c, LAFIS_ERR_ARG, "gallery shard too large for 32-bit offsets");
-    // Every parser thread uploads its own part straight to its place in device staging arrays (its own stream, so the
-    // pageable copies of different threads overlap); no consolidated host copy of the gallery is ever built.
-    LAFIS_CUDA(c, cudaSetDevice(c->device));
-    void* dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    const size_t bytes[8] = {2 * tot_m, 2 * tot_m, 4 * tot_m, 4 * tot_m * kDesLen, 2 * tot_t, 2 * tot_t, 4 * tot_t, 16 * tot_t};
-    auto free_dev = [&]() {
-        for (void*& d : dev) {
-            if (d) cudaFree(d);
-            d = nullptr;
-        }
-    };
-    for (int k = 0; k < 8; ++k) {
-        const cudaError_t e = cudaMalloc(&dev[k], std::max<size_t>(bytes[k], 16));
-        if (e != cudaSuccess) {
-            free_dev();
-            return fail(c, LAFIS_ERR_CUDA, "gallery staging: cudaMalloc failed: %s", cudaGetErrorString(e));
-        }
-    }
-    std::vector<int> up_err(n_threads, 0);
+
+    // pool capacity: what a file can contribute is bounded by its size (+ alignment padding per piece)
+    std::vector<unsigned long long> part_bytes(n_threads, 0);
     run_parallel([&](int i) {
-        const Part& P = parts[i];
-        cudaStream_t s_ = nullptr;
-        bool ok = cudaSetDevice(c->device) == cudaSuccess && cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking) == cudaSuccess;
-        auto cp = [&](int k, size_t elem_off, size_t elem_bytes, const void* src, size_t n_bytes) {
-            if (ok && n_bytes)
-                ok = cudaMemcpyAsync((char*)dev[k] + elem_off * elem_bytes, src, n_bytes, cudaMemcpyHostToDevice, s_) == cudaSuccess;
-        };
-        cp(0, part_m[i], 2, P.mx.data(), 2 * P.mx.size());
-        cp(1, part_m[i], 2, P.my.data(), 2 * P.my.size());
-        cp(2, part_m[i], 4, P.mori.data(), 4 * P.mori.size());
-        cp(3, part_m[i], 4 * kDesLen, P.mdes.data(), 4 * P.mdes.size());
-        cp(4, part_t[i], 2, P.tx.data(), 2 * P.tx.size());
-        cp(5, part_t[i], 2, P.ty.data(), 2 * P.ty.size());
-        cp(6, part_t[i], 4, P.tori.data(), 4 * P.tori.size());
-        cp(7, part_t[i], 16, P.codes.data(), P.codes.size());
-        if (s_) {
-            ok = cudaStreamSynchronize(s_) == cudaSuccess && ok;
-            cudaStreamDestroy(s_);
+        unsigned long long tot = 0;
+        for (int t = range_lo(i); t < range_lo(i + 1); ++t) {
+            std::error_code ec;
+            const auto sz = std::filesystem::file_size(paths[lo + t], ec);
+            tot += (ec ? 0ull : (unsigned long long)sz) + 8 * 16;
         }
-        up_err[i] = ok ? 0 : 1;
-        parts[i] = Part();  // release the part as soon as it has been uploaded
+        part_bytes[i] = tot;
     });
-    for (int e : up_err)
-        if (e) {
-            free_dev();
-            return fail(c, LAFIS_ERR_CUDA, "gallery staging: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    unsigned long long pool_cap = 0;
+    for (unsigned long long b : part_bytes) pool_cap += b;
+    constexpr size_t kSlotBytes = (size_t)8 << 20;  // > the largest template (2000 minutiae + 2000 texture points: 0.9 MB)
+    constexpr int kRing = 3;
+    unsigned char* d_pool = nullptr;
+    LAFIS_CUDA(c, cudaMalloc(&d_pool, std::max<unsigned long long>(pool_cap, 16)));
+    std::atomic<unsigned long long> pool_used{0};
+
+    std::vector<PoolRec> rec(m);
+    std::vector<int8_t> status(m);
+    std::vector<std::string> kept(m);
+    std::vector<int> thread_err(n_threads, 0);
+    run_parallel([&](int i) {
+        cudaStream_t s_ = nullptr;
+        unsigned char* slot[kRing] = {nullptr, nullptr, nullptr};
+        cudaEvent_t done[kRing] = {nullptr, nullptr, nullptr};
+        bool ok = cudaSetDevice(c->device) == cudaSuccess && cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < kRing && ok; ++k)
+            ok = cudaMallocHost(&slot[k], kSlotBytes) == cudaSuccess && cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) == cudaSuccess;
+        int cur = 0, first_in_slot = range_lo(i);
+        size_t used = 0;
+        auto flush = [&](int t_end) {  // ship templates [first_in_slot, t_end) packed in slot[cur]
+            if (!ok || used == 0) {
+                first_in_slot = t_end;
+                return;
+            }
+            const unsigned long long at = pool_used.fetch_add(used);
+            if (at + used > pool_cap) {
+                ok = false;
+                return;
+            }
+            ok = cudaMemcpyAsync(d_pool + at, slot[cur], used, cudaMemcpyHostToDevice, s_) == cudaSuccess &&
+                 cudaEventRecord(done[cur], s_) == cudaSuccess;
+            for (int t = first_in_slot; t < t_end; ++t) {
+                rec[t].minu_at += at;
+                rec[t].tex_at += at;
+            }
+            first_in_slot = t_end;
+            cur = (cur + 1) % kRing;
+            used = 0;
+            if (ok) ok = cudaEventSynchronize(done[cur]) == cudaSuccess;  // the buffer about to be reused (no-op when never used)
+        };
+        for (int t = range_lo(i); t < range_lo(i + 1) && ok; ++t) {
+            RolledTemplate R;
+            read_rolled_dat(paths[lo + t], R);
+            kept[t] = paths[lo + t];
+            status[t] = (int8_t)R.status;
+            const size_t nm = R.minu.x.size();
+            const size_t nt = std::min<size_t>(R.tex.x.size(), (size_t)kMaxTexture);  // matcher.cpp:546-547
+            const size_t need = pool_minu_bytes(nm) + pool_tex_bytes(nt);
+            if (need > kSlotBytes) {
+                ok = false;
+                break;
+            }
+            if (used + need > kSlotBytes) flush(t);
+            unsigned char* p = slot[cur] + used;
+            rec[t].minu_at = used;
+            rec[t].n_minu = (uint32_t)nm;
+            std::memcpy(p, R.minu.x.data(), 2 * nm);
+            std::memcpy(p + pool_align(2 * nm), R.minu.y.data(), 2 * nm);
+            std::memcpy(p + 2 * pool_align(2 * nm), R.minu.ori.data(), 4 * nm);
+            std::memcpy(p + 2 * pool_align(2 * nm) + pool_align(4 * nm), R.minu.des.data(), 4 * (size_t)kDesLen * nm);
+            p += pool_minu_bytes(nm);
+            rec[t].tex_at = used + pool_minu_bytes(nm);
+            rec[t].n_tex = (uint32_t)nt;
+            std::memcpy(p, R.tex.x.data(), 2 * nt);
+            std::memcpy(p + pool_align(2 * nt), R.tex.y.data(), 2 * nt);
+            std::memcpy(p + 2 * pool_align(2 * nt), R.tex.ori.data(), 4 * nt);
+            std::memcpy(p + 2 * pool_align(2 * nt) + pool_align(4 * nt), R.tex.codes.data(), 16 * nt);
+            used += need;
         }
-    lafis_packed_gallery g{};
-    g.n_templates = m;
-    g.minu_off = minu_off.data();
-    g.minu_x = static_cast<const int16_t*>(dev[0]);
-    g.minu_y = static_cast<const int16_t*>(dev[1]);
-    g.minu_ori = static_cast<const float*>(dev[2]);
-    g.minu_des = static_cast<const float*>(dev[3]);
-    g.tex_off = tex_off.data();
-    g.tex_x = static_cast<const int16_t*>(dev[4]);
-    g.tex_y = static_cast<const int16_t*>(dev[5]);
-    g.tex_ori = static_cast<const float*>(dev[6]);
-    g.tex_codes = static_cast<const uint8_t*>(dev[7]);
-    g.status = status.data();
-    g.on_device = 1;
-    const double up_ms = ms_since(t_up);
+        flush(range_lo(i + 1));
+        if (s_) ok = cudaStreamSynchronize(s_) == cudaSuccess && ok;
+        for (int k = 0; k < kRing; ++k) {
+            if (done[k]) cudaEventDestroy(done[k]);
+            if (slot[k]) cudaFreeHost(slot[k]);
+        }
+        if (s_) cudaStreamDestroy(s_);
+        thread_err[i] = ok ? 0 : 1;
+    });
+    const double stream_ms = ms_since(t_all);
+    for (int e : thread_err)
+        if (e) {
+            cudaFree(d_pool);
+            free_gallery(c);
+            return fail(c, LAFIS_ERR_CUDA, "gallery ingest: staging or host-to-device copy failed: %s",
+                        cudaGetErrorString(cudaGetLastError()));
+        }
+
+    // ---- resident arrays + re-layout from the pool ----
     const auto t_set = now();
-    int rc = lafis_gallery_set_packed(c, &g, (uint32_t)lo);
+    std::vector<uint32_t> dst_minu_off(m + 1), dst_tex_off(m + 1);
+    std::vector<uint16_t> minu_n(m);
+    int max_nR = 0, max_nRt = 0;
+    uint64_t algo = 0;
+    dst_minu_off[0] = dst_tex_off[0] = 0;
+    for (int t = 0; t < m; ++t) {
+        const uint32_t nm = rec[t].n_minu, nt = rec[t].n_tex;
+        minu_n[t] = (uint16_t)nm;
+        dst_minu_off[t + 1] = dst_minu_off[t] + ((nm + 3u) & ~3u);
+        dst_tex_off[t + 1] = dst_tex_off[t] + nt;
+        max_nR = std::max(max_nR, (int)nm);
+        max_nRt = std::max(max_nRt, (int)nt);
+        if ((status[t] == LAFIS_TPL_OK || status[t] == LAFIS_TPL_TRUNCATED) && nm == 0 && nt == 0) status[t] = LAFIS_TPL_EMPTY;
+        algo += 392ull * nm + 24ull * nt;
+        if ((size_t)dst_minu_off[t + 1] > 0x7fffffffu || (size_t)dst_tex_off[t + 1] > 0x7fffffffu) {
+            cudaFree(d_pool);
+            free_gallery(c);
+            return fail(c, LAFIS_ERR_ARG, "gallery shard too large for 32-bit offsets");
+        }
+    }
+    const uint32_t dst_minu_tot = dst_minu_off[m], dst_tex_tot = dst_tex_off[m];
+    DeviceGallery& G = c->gal;
+    PoolRec* d_rec = nullptr;
+    auto bail = [&](cudaError_t e, const char* what) {
+        cudaFree(d_pool);
+        cudaFree(d_rec);
+        free_gallery(c);
+        return fail(c, LAFIS_ERR_CUDA, "gallery ingest: %s failed: %s", what, cudaGetErrorString(e));
+    };
+#define LAFIS_CUDA_I(expr)                           \
+    do {                                             \
+        cudaError_t e__ = (expr);                    \
+        if (e__ != cudaSuccess) return bail(e__, #expr); \
+    } while (0)
+    G.n = m;
+    LAFIS_CUDA_I(cudaMalloc(&d_rec, sizeof(PoolRec) * (size_t)m));
+    LAFIS_CUDA_I(cudaMalloc(&G.minu_off, 4ull * (m + 1)));
+    LAFIS_CUDA_I(cudaMalloc(&G.minu_n, 2ull * m));
+    LAFIS_CUDA_I(cudaMalloc(&G.minu_xy, sizeof(short2) * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_I(cudaMalloc(&G.minu_ori, 4ull * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_I(cudaMalloc(&G.minu_desT, 4ull * kDesLen * std::max<size_t>(dst_minu_tot, 4)));
+    LAFIS_CUDA_I(cudaMalloc(&G.tex_off, 4ull * (m + 1)));
+    LAFIS_CUDA_I(cudaMalloc(&G.tex_xy, sizeof(short2) * std::max<size_t>(dst_tex_tot, 4)));
+    LAFIS_CUDA_I(cudaMalloc(&G.tex_ori, 4ull * std::max<size_t>(dst_tex_tot, 4)));
+    LAFIS_CUDA_I(cudaMalloc(&G.tex_codes, 16ull * ((size_t)dst_tex_tot + 32)));
+    LAFIS_CUDA_I(cudaMalloc(&G.status, (size_t)m));
+    LAFIS_CUDA_I(cudaMemcpyAsync(d_rec, rec.data(), sizeof(PoolRec) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_I(cudaMemcpyAsync(G.minu_off, dst_minu_off.data(), 4ull * (m + 1), cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_I(cudaMemcpyAsync(G.minu_n, minu_n.data(), 2ull * m, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_I(cudaMemcpyAsync(G.tex_off, dst_tex_off.data(), 4ull * (m + 1), cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_I(cudaMemcpyAsync(G.status, status.data(), (size_t)m, cudaMemcpyHostToDevice, c->stream));
+    LAFIS_CUDA_I(cudaMemsetAsync(G.tex_codes + dst_tex_tot, 0, 16ull * 32, c->stream));
+    PoolRelayoutParams rp;
+    rp.pool = d_pool;
+    rp.rec = d_rec;
+    rp.minu_off = G.minu_off;
+    rp.tex_off = G.tex_off;
+    rp.minu_xy = G.minu_xy;
+    rp.minu_ori = G.minu_ori;
+    rp.minu_desT = G.minu_desT;
+    rp.tex_xy = G.tex_xy;
+    rp.tex_ori = G.tex_ori;
+    rp.tex_codes = G.tex_codes;
+    relayout_minutiae_pool_kernel<<<m, 256, 0, c->stream>>>(rp);
+    copy_texture_pool_kernel<<<m, 256, 0, c->stream>>>(rp);
+    c->stats.kernel_launches += 2;
+    LAFIS_CUDA_I(cudaGetLastError());
+    LAFIS_CUDA_I(cudaStreamSynchronize(c->stream));
+#undef LAFIS_CUDA_I
+    cudaFree(d_pool);
+    cudaFree(d_rec);
+    c->h_status.swap(status);
+    c->h_minu_off.swap(dst_minu_off);
+    c->h_minu_n.swap(minu_n);
+    c->h_tex_off.swap(dst_tex_off);
+    c->max_nR = max_nR;
+    c->max_nRt = max_nRt;
+    c->algo_bytes = algo;
+    c->paths.swap(kept);
+    size_work_budget(c);
     if (timing)
-        fprintf(stderr, "lafis ingest: %d files, %d threads: parse %.1f ms, upload %.1f ms, re-layout %.1f ms\n", m, n_threads,
-                parse_ms, up_ms, ms_since(t_set));
-    free_dev();
-    if (rc == LAFIS_OK) c->paths.swap(kept);
-    return rc;
+        fprintf(stderr,
+                "lafis ingest: %d files, %d threads: parse + pinned upload %.1f ms (%.2f GB staged), re-layout %.1f ms, total %.1f ms "
+                "= %.0f templates/s\n",
+                m, n_threads, stream_ms, (double)pool_used.load() / 1e9, ms_since(t_set), ms_since(t_all),
+                m / (ms_since(t_all) / 1e3));
+    return LAFIS_OK;
 }
 
 int lafis_gallery_load_dir(lafis_ctx* c, const char* dir, int shard_rank, int shard_count) {

@@ -103,6 +103,7 @@ struct lafis_ctx {
     std::string err;
     int sm_count = 148;
     size_t work_budget = (size_t)24 << 30;
+    bool work_budget_fixed = false;  // LAFIS_WORK_BYTES given: otherwise sized from the free device memory per match
 
     float* d_codebook = nullptr;  // [16][256][6]
     float* d_table = nullptr;     // [50*50]

@@ -463,35 +463,41 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
     }
     __syncthreads();
 
-    // ---- pass 1: histogram of the estimates ----
+    // ---- pass 1: estimates; every thread keeps the largest of its own.  The K-th largest of those <= 384 thread
+    //      maxima (distinct elements) is a lower bound of the K-th largest estimate overall, and with ~25 elements per
+    //      thread it sits at the ~1.5 % quantile: ~150 of the 9,600 estimates lie above it.  Only the thread maxima go
+    //      through the histogram (<= 384 shared-memory atomics per job instead of one per positive element). ----
     const int M = nL * nR;
     const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
-    for (int i = warp; i < nL; i += NW) {
-        const float l = lsum[i];
-        for (int j = lane; j < nR; j += 32) {
-            const float s = Ssm[i * ld + j];
-            if (s > 0.0f) {
-                const float a = approx_key(s, l, rsum[j]);
-                Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
-                const uint32_t hb = __float_as_uint(a) >> 17;
-                atomicAdd(&hist[hb > kSelBinBase ? min(hb - kSelBinBase, (uint32_t)(kSelBins - 1)) : 0u], 1);
+    {
+        float mymax = 0.0f;
+        int mypos = 0;
+        for (int i = warp; i < nL; i += NW) {
+            const float l = lsum[i];
+            for (int j = lane; j < nR; j += 32) {
+                const float s = Ssm[i * ld + j];
+                if (s > 0.0f) {
+                    const float a = approx_key(s, l, rsum[j]);
+                    Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
+                    mymax = fmaxf(mymax, a);
+                    ++mypos;
+                }
             }
         }
-    }
-    __syncthreads();
-    if (warp == 0) {  // number of positive values = histogram total
-        int tot = 0;
-        for (int b = lane; b < kSelBins; b += 32) tot += hist[b];
-        tot = __reduce_add_sync(0xffffffffu, tot);
-        if (lane == 0) s_npos = tot;
+        if (mymax > 0.0f) {
+            const uint32_t hb = __float_as_uint(mymax) >> 17;
+            atomicAdd(&hist[hb > kSelBinBase ? min(hb - kSelBinBase, (uint32_t)(kSelBins - 1)) : 0u], 1);
+        }
+        mypos = __reduce_add_sync(0xffffffffu, mypos);
+        if (lane == 0 && mypos) atomicAdd(&s_npos, mypos);
     }
     __syncthreads();
     if (s_npos < K) {  // the 120th value is a zero: ties among zeros decide the order
         if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
         return;
     }
-    if (warp == 0) {  // bin of the K-th largest estimate, scanning 32-bin chunks from the top
-        int above = 0, bin = 0;
+    if (warp == 0) {  // bin of the K-th largest thread maximum, scanning 32-bin chunks from the top
+        int above = 0, bin = 0;  // fewer than K positive thread maxima: bin 0, every positive estimate is a candidate
         for (int c = kSelBins / 32 - 1; c >= 0; --c) {
             const int h = hist[c * 32 + lane];
             const int tot = __reduce_add_sync(0xffffffffu, h);
@@ -512,7 +518,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
         }
         if (lane == 0) {
             s_bin = bin;
-            // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side)
+            // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side): at least K
+            // estimates (thread maxima) lie at or above the edge, so the exact K-th largest value does too
             // (bin 0 collects everything below 2^-16: its lower edge is 0)
             s_thr = bin > 0 ? __uint_as_float(((uint32_t)bin + kSelBinBase) << 17) * (1.0f - 4e-6f) : 0.0f;
         }

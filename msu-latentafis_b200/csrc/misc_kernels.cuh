@@ -260,4 +260,68 @@ __global__ void copy_texture_kernel(TexCopyParams P) {
     }
 }
 
+// ---- ingest from the parser threads' device pool -----------------------------------------------------
+// lafis_gallery_load_files: every parser thread ships blocks of parsed templates through pinned ring buffers into one
+// device pool; a template's pieces lie back to back at 16-byte aligned offsets:
+//   minutiae: x[n] i16 | y[n] i16 | ori[n] f32 | des[n][96] f32 (row-major, as in the file)
+//   texture : x[n] i16 | y[n] i16 | ori[n] f32 | codes[n][16] u8
+// The two kernels below produce the resident layout (k-major descriptors, short2 coordinates, uint4 code words)
+// straight from the pool.  grid = templates.
+struct PoolRec {
+    unsigned long long minu_at, tex_at;  // byte offsets into the pool
+    uint32_t n_minu, n_tex;              // points kept (texture: <= 1000, matcher.cpp:546-547)
+};
+__host__ __device__ inline size_t pool_align(size_t v) { return (v + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t pool_minu_bytes(size_t n) { return pool_align(2 * n) * 2 + pool_align(4 * n) + pool_align(4 * 96 * n); }
+__host__ __device__ inline size_t pool_tex_bytes(size_t n) { return pool_align(2 * n) * 2 + pool_align(4 * n) + pool_align(16 * n); }
+
+struct PoolRelayoutParams {
+    const unsigned char* pool;
+    const PoolRec* rec;
+    const uint32_t* minu_off;  // resident (padded) offsets
+    const uint32_t* tex_off;
+    short2* minu_xy;
+    float* minu_ori;
+    float* minu_desT;
+    short2* tex_xy;
+    float* tex_ori;
+    uint4* tex_codes;
+};
+
+__global__ void relayout_minutiae_pool_kernel(PoolRelayoutParams P) {
+    const int g = blockIdx.x;
+    const PoolRec r = P.rec[g];
+    const uint32_t n = r.n_minu, d0 = P.minu_off[g], np = P.minu_off[g + 1] - d0;
+    const unsigned char* base = P.pool + r.minu_at;
+    const int16_t* x = reinterpret_cast<const int16_t*>(base);
+    const int16_t* y = reinterpret_cast<const int16_t*>(base + pool_align(2 * (size_t)n));
+    const float* ori = reinterpret_cast<const float*>(base + 2 * pool_align(2 * (size_t)n));
+    const float* des = reinterpret_cast<const float*>(base + 2 * pool_align(2 * (size_t)n) + pool_align(4 * (size_t)n));
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+        P.minu_xy[d0 + i] = i < n ? make_short2(x[i], y[i]) : make_short2(0, 0);
+        P.minu_ori[d0 + i] = i < n ? ori[i] : 0.0f;
+    }
+    float* dst = P.minu_desT + (size_t)96 * d0;
+    for (uint32_t e = threadIdx.x; e < 96 * np; e += blockDim.x) {
+        const uint32_t k = e / np, i = e - k * np;
+        dst[e] = (i < n) ? des[(size_t)i * 96 + k] : 0.0f;
+    }
+}
+
+__global__ void copy_texture_pool_kernel(PoolRelayoutParams P) {
+    const int g = blockIdx.x;
+    const PoolRec r = P.rec[g];
+    const uint32_t n = r.n_tex, d0 = P.tex_off[g];
+    const unsigned char* base = P.pool + r.tex_at;
+    const int16_t* x = reinterpret_cast<const int16_t*>(base);
+    const int16_t* y = reinterpret_cast<const int16_t*>(base + pool_align(2 * (size_t)n));
+    const float* ori = reinterpret_cast<const float*>(base + 2 * pool_align(2 * (size_t)n));
+    const uint4* codes = reinterpret_cast<const uint4*>(base + 2 * pool_align(2 * (size_t)n) + pool_align(4 * (size_t)n));
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        P.tex_xy[d0 + i] = make_short2(x[i], y[i]);
+        P.tex_ori[d0 + i] = ori[i];
+        P.tex_codes[d0 + i] = codes[i];
+    }
+}
+
 }  // namespace lafis

@@ -85,16 +85,22 @@ def synthetic_codebook(seed: int = 7) -> np.ndarray:
 
 
 def pq_encode(des: np.ndarray, codewords: np.ndarray) -> np.ndarray:
-    """TrainedPQEncoder.encode_multi (extraction/descriptor_PQ.py:19-27): per sub-quantizer the
-    index of the nearest centroid (scipy.cluster.vq.vq; first minimum wins)."""
-    des = np.asarray(des, dtype=np.float64)
+    """TrainedPQEncoder.encode_multi (extraction/descriptor_PQ.py:19-27): per sub-quantizer the index of the nearest
+    centroid, first minimum wins.  Same arithmetic as the device encoder (pq_encode_kernel): fp32 squared differences
+    accumulated in dimension order, so that the Python tooling and the GPU produce identical codes.  The reference's
+    scipy.cluster.vq.vq evaluates |o|^2 + |c|^2 - 2 o.c through BLAS for sub-vectors of 5+ dimensions; the two can
+    only disagree where two centroids are equidistant to within fp32 rounding (tests/test_pq_encode.py)."""
+    des = np.ascontiguousarray(des, dtype=np.float32)
     n = des.shape[0]
     subs, _, sd = codewords.shape
     codes = np.empty((n, subs), dtype=np.uint8)
-    cw = codewords.astype(np.float64)
+    cw = np.ascontiguousarray(codewords, dtype=np.float32)
     for m in range(subs):
         sub = des[:, m * sd:(m + 1) * sd]
-        d = ((sub[:, None, :] - cw[m][None, :, :]) ** 2).sum(-1)
+        d = np.zeros((n, cw.shape[1]), np.float32)
+        for k in range(sd):  # dist = fl(dist + fl(t * t)), t = fl(x - c), k ascending
+            t = sub[:, k:k + 1] - cw[m][None, :, k]
+            d = d + t * t
         codes[:, m] = np.argmin(d, axis=1).astype(np.uint8)
     return codes
 
