@@ -776,10 +776,10 @@ int lafis_latents_from_packed(lafis_ctx* c, const lafis_packed_latents* p, lafis
         L->status[q] = st;
         // The texture score lands in score[n_minu_templates] (matcher.cpp:414).  The fusion (:188, :293) reads
         // score[0] + score[1] + score[2] + score[28] * 0.3: with 28 minutiae templates the texture score is the
-        // weighted term (mode 1); with 0, 1 or 2 minutiae templates (and enough texture templates for score[28] to
-        // exist) it sits in one of the three unweighted slots, whose minutiae scores are then all 0 (mode 2).  With
+        // weighted term (mode 1); with k = 0, 1 or 2 minutiae templates (and enough texture templates for score[28] to
+        // exist) it sits in the unweighted slot score[k], the minutiae scores being all 0 then (mode 2 + k).  With
         // any other template count it is never read, so it is not computed.
-        L->tex_weighted[q] = (nt >= 1 && st == LAFIS_OK) ? (nm == 28 ? 1 : (nm >= 0 && nm <= 2) ? 2 : 0) : 0;
+        L->tex_weighted[q] = (nt >= 1 && st == LAFIS_OK) ? (nm == 28 ? 1 : (nm >= 0 && nm <= 2) ? 2 + nm : 0) : 0;
         int ntp = nt > 0 ? (int)(p->tex_off[q + 1] - p->tex_off[q]) : 0;
         if (ntp > kMaxTexture) ntp = kMaxTexture;  // matcher.cpp:544-545
         if (!L->tex_weighted[q]) ntp = 0;

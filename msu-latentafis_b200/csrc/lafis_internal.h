@@ -63,7 +63,7 @@ struct CommState;  // sharded.cu: NCCL communicator of a context
 struct lafis_latents {
     int n = 0;
     std::vector<int> status;            // LAFIS_OK / LAFIS_LATENT_EMPTY / LAFIS_ERR_LATENT_LAYOUT
-    std::vector<int> tex_weighted;      // 0: texture score not fused, 1: fused as score[28] * 0.3, 2: lands in score[0..2] (weight 1)
+    std::vector<int> tex_weighted;      // 0: texture score not read, 1: it is score[28] (weight 0.3), 2 + k: it is score[k], k = 0..2 (weight 1)
     std::vector<int> n_minu_templates;  // as in the file (slot presence for the drivers)
     // host staging, already in device layout
     int lt_stride = 8;

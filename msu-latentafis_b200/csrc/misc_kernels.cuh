@@ -16,9 +16,9 @@ namespace lafis {
 // keep -1: latent not matchable (One2One_matching_selected_templates returns 1) or rolled template
 // empty / failed to load (returns 2, matcher.cpp:173-177, :184-187).
 struct FuseParams {
-    const float* comp;         // [Q][G][4]
+    float* comp;               // [Q][G][4]: minutiae slots 0..2 and the texture score, rewritten as score[0], score[1], score[2], score[28]
     const int* lat_status;     // [Q]
-    const int* tex_weighted;   // [Q] 0 / 1 (score[28], weight 0.3) / 2 (a slot of score[0..2], weight 1)
+    const int* tex_weighted;   // [Q] 0: texture score not read / 1: it is score[28] (weight 0.3) / 2 + k: it is score[k], k = 0..2 (weight 1)
     const int8_t* gal_status;  // [G]
     int Q, G;
     float* final_scores;       // [Q][G]
@@ -31,13 +31,20 @@ __global__ void fuse_kernel(FuseParams P) {
     float out = -1.0f;
     const int8_t gs = P.gal_status[g];
     if (P.lat_status[q] == 0 && (gs == 0 || gs == 2)) {
-        const float4 c = *reinterpret_cast<const float4*>(P.comp + e * 4);
+        float4 c = *reinterpret_cast<const float4*>(P.comp + e * 4);
         const int mode = P.tex_weighted[q];
-        float s0 = c.x;
-        if (mode == 2) s0 = c.w;  // <= 2 minutiae templates: the texture score IS one of score[0..2], the others are 0
-        const float s012 = f_add(f_add(s0, c.y), c.z);
-        const float s28 = mode == 1 ? c.w : 0.0f;
-        out = (float)((double)s012 + (double)s28 * 0.3);
+        if (mode != 1) {
+            // <= 2 minutiae templates: the texture score IS score[n_minu_templates] (matcher.cpp:414), one of the three
+            // unweighted terms (the minutiae scores are all 0 then); any other count: it is never read
+            const float t = c.w;
+            c.w = 0.0f;
+            if (mode == 2) c.x = t;
+            else if (mode == 3) c.y = t;
+            else if (mode == 4) c.z = t;
+            *reinterpret_cast<float4*>(P.comp + e * 4) = c;
+        }
+        const float s012 = f_add(f_add(c.x, c.y), c.z);
+        out = (float)((double)s012 + (double)c.w * 0.3);
     }
     P.final_scores[e] = out;
 }

@@ -563,8 +563,11 @@ float lo_fuse(float s0, float s1, float s2, float s28) {
 /* One2One_matching_selected_templates + fusion, matcher.cpp:376-417 and :179-189.
  * latent_minu: the latent's NON-EMPTY minutiae templates in file order (the loader drops empty
  * ones, matcher.cpp:834-836).  Returns 1 / 2 like the reference; -100 when score[28] would be read
- * out of bounds (latent without exactly 28 minutiae templates + >=1 texture template), which is
- * outside the parity domain.  comp = {score[0], score[1], score[2], score[28]}. */
+ * out of bounds (fewer than 29 template slots), which is outside the parity domain.
+ * comp = {score[0], score[1], score[2], score[28]} of the reference's score vector: minutiae score i
+ * lands in score[i] (:406), the texture score in score[n_latent_minu] (:414) - i.e. in score[28] for
+ * the regular 28-template latent, in one of score[0..2] for a latent with at most 2 minutiae
+ * templates, and in a slot the fusion never reads otherwise. */
 int lo_score_pair(const lo_template_t* latent_minu, int n_latent_minu, const lo_template_t* latent_tex,
                   int n_latent_tex, const float* latent_lut, const lo_template_t* rolled_minu, int n_rolled_minu,
                   const lo_template_t* rolled_tex, int n_rolled_tex, const float* table, int subs, int clusters,
@@ -574,13 +577,15 @@ int lo_score_pair(const lo_template_t* latent_minu, int n_latent_minu, const lo_
     *final_score = -1.0f;
     if (n_latent_minu <= selected[0] && n_latent_tex <= 0) return 1;
     if (n_rolled_minu <= 0 && n_rolled_tex <= 0) return 2;
-    if (n_latent_minu + n_latent_tex < 29 || n_latent_minu != 28) return -100;
+    if (n_latent_minu + n_latent_tex < 29) return -100;
     for (int i = 0; i < 3 && n_rolled_minu > 0; ++i) {
         if (n_latent_minu <= selected[i]) continue;
         comp[i] = lo_minutiae_score(&latent_minu[selected[i]], &rolled_minu[0]);
     }
-    if (n_latent_tex > 0 && n_rolled_tex > 0)
-        comp[3] = lo_texture_score(&latent_tex[0], latent_lut, &rolled_tex[0], table, subs, clusters);
+    if (n_latent_tex > 0 && n_rolled_tex > 0 && (n_latent_minu == 28 || n_latent_minu <= 2)) {
+        const float t = lo_texture_score(&latent_tex[0], latent_lut, &rolled_tex[0], table, subs, clusters);
+        comp[n_latent_minu == 28 ? 3 : n_latent_minu] = t;
+    }
     *final_score = lo_fuse(comp[0], comp[1], comp[2], comp[3]);
     return 0;
 }

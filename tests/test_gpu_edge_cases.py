@@ -227,3 +227,25 @@ def test_oversized_templates_across_pipeline_chunks(pkg, built, golden, oracle, 
     monkeypatch.setenv("LAFIS_WORK_BYTES", "1500000")
     st = _run(pkg, cb, latents, rolled, oracle)
     assert st["minu_big_jobs"] == 3 * 9 + 3 * 3   # the oversized latent against everything + the other against 3 templates
+
+
+def test_texture_score_in_an_unweighted_slot(pkg, matcher, golden, oracle):
+    """Latents with 1 or 2 minutiae templates: the reference stores the texture score in score[1], score[2] (matcher.cpp:414)
+    and fuses it with weight 1 (:188); with 5 minutiae templates it is never read.  Library vs oracle, bit for bit."""
+    from test_oracle_vs_reference import _odd_layout_latents
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(4100 + g, n_minu=50, n_tex=150) for g in range(3)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = _odd_layout_latents(T, raws)
+    matcher.set_gallery(pkg.pack_rolled(rolled))
+    L = matcher.latents_from_packed(pkg.pack_latents(latents))
+    assert [L.status(q) for q in range(3)] == [0, 0, 0]
+    out = matcher.match(L, topk=2, want_components=True)
+    rc, comp, fin = oracle_scores(oracle, T, latents, rolled, cb)
+    assert (rc == 0).all()
+    assert np.array_equal(out["components"], comp), (out["components"], comp)
+    assert np.array_equal(out["scores"], fin)
+    for k in range(2):
+        assert out["hits"][k]["index"][0] == k and fin[k, k] > 0
+    assert np.array_equal(fin[2], comp[2, :, 1]) and (comp[2, :, 3] == 0).all()  # texture score never read

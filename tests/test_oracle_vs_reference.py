@@ -34,11 +34,7 @@ def test_oracle_reproduces_golden_pairs(pkg, oracle, golden, tmp_path):
             if want_rc != 0:
                 assert rc == want_rc and fin == -1.0, (l, g)
                 continue
-            if str(l) == "lG_30templates":
-                # 30 minutiae templates: score[28] is a never-written minutiae slot (matcher.cpp:188),
-                # which the oracle reports as "outside the parity domain"
-                assert rc == -100
-                continue
+            # (lG_30templates: 30 minutiae templates, score[28] is a never-written minutiae slot, matcher.cpp:188)
             assert rc == 0
             assert np.array_equal(comp, golden["pair_comp"][i, j]), (l, g, comp, golden["pair_comp"][i, j])
             assert fin == golden["pair_final"][i, j], (l, g)
@@ -102,3 +98,50 @@ def test_oracle_sort_permutation_matches_libstdcxx(oracle):
             if levels:
                 key = np.round(key * levels) / levels  # many exact ties
             assert np.array_equal(oracle.std_sort_desc(key), rb.std_sort_desc(key)), (n, levels)
+
+
+def _odd_layout_latents(T, raws):
+    """Latents whose template counts put the texture score somewhere else than score[28] (matcher.cpp:414, :188):
+    (minutiae templates, texture templates) = (1, 28), (2, 27) -> the texture score is score[1], score[2] and is
+    fused with weight 1; (5, 24) -> it is score[5], which the fusion never reads.  (A latent file without any
+    minutiae template cannot be written by the reference's writer: descriptor_PQ.py:92-95 emits the empty file.)"""
+    out = []
+    for k, (nm, nt) in enumerate(((1, 28), (2, 27), (5, 24))):
+        full = T.synth_latent(300 + k, raws[k], n_minu=30, n_tex_pts=60)
+        tex = full.tex[0]
+        out.append(T.FPTemplate(h=full.h, w=full.w, blkH=full.blkH, blkW=full.blkW, minu=full.minu[:nm],
+                                tex=[tex] + [T.TextureTemplate(tex.x[:3], tex.y[:3], tex.ori[:3], tex.des[:3])] * (nt - 1)))
+    return out
+
+
+def test_texture_score_in_an_unweighted_slot(oracle, golden, tmp_path):
+    """Oracle port against the reference itself on latents with 1, 2 and 5 minutiae templates."""
+    rb = _refbind()
+    if rb is None:
+        pytest.skip("oracle/_ref not built")
+    import __graft_entry__ as entry
+    T = entry.load_package().templates
+    cb = golden["codebook"]
+    cbp = str(tmp_path / "cb.dat")
+    T.write_codebook(cbp, cb)
+    R = rb.RefMatcher(cbp)
+    raws = [T.synth_rolled_raw(4100 + g, n_minu=50, n_tex=150) for g in range(3)]
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    for k, lat in enumerate(_odd_layout_latents(T, raws)):
+        lp = str(tmp_path / f"l{k}.dat")
+        T.write_template(lp, lat)
+        lh, _ = R.load_latent(lp)
+        OL = oracle.OracleLatent(lat, cb)
+        for g, r in enumerate(rolled):
+            rp = str(tmp_path / f"r{g}.dat")
+            T.write_template(rp, r)
+            rh, _ = R.load_rolled(rp)
+            rc1, comp1, fin1 = R.score_pair(lh, rh)
+            rc2, comp2, fin2 = oracle.score_pair(OL, oracle.OracleRolled(r))
+            assert rc1 == rc2 == 0, (k, g, rc1, rc2)
+            assert np.array_equal(comp1, comp2) and fin1 == fin2, (k, g, comp1, comp2)
+            if k < 2:
+                assert comp1[3] == 0 and fin1 == comp1[k + 1] and (g != k or fin1 > 0)
+            else:  # 5 minutiae templates: template 2 is matched (score[1]), the texture score (score[5]) is never read
+                assert comp1[3] == 0 and comp1[0] == 0 and comp1[2] == 0 and fin1 == comp1[1]
+    R.close()
