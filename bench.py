@@ -171,9 +171,9 @@ def host_sample(T, cb, n, n_latents=1, encoder=None, profile="iid"):
     """n host-side synthetic rolled prints (seeds 1000+g) and latents mated to the first n_latents of them.
     `encoder` (descriptors -> PQ codes) replaces the numpy nearest-centroid search when given."""
     raws = [T.synth_rolled_raw(g) for g in range(n)]
-    if profile == "hard":
+    if profile != "iid":
         from msu_latentafis_b200.synth import harden_raw
-        raws = [harden_raw(r, g) for g, r in enumerate(raws)]
+        raws = [harden_raw(r, g, profile) for g, r in enumerate(raws)]
     if encoder is None:
         rolled = [T.rolled_from_raw(r, cb) for r in raws]
     else:
@@ -655,7 +655,7 @@ def main():
     ap.add_argument("--latents", type=int, default=1)
     ap.add_argument("--gallery-per-gpu", type=int, default=0, help="default: 100000 on one GPU, 125000 per GPU on several")
     ap.add_argument("--topk", type=int, default=100)
-    ap.add_argument("--profile", default="iid", choices=["iid", "hard"])
+    ap.add_argument("--profile", default="iid", choices=["iid", "hard", "harder"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--parity-sample", type=int, default=1024)
     ap.add_argument("--no-sub", action="store_true", help="skip the 27- / 256-latent sub-results and the command-line legs")

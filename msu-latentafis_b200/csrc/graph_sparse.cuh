@@ -30,11 +30,11 @@ template <bool LOOKUP>
 struct SparseGeom;
 template <>
 struct SparseGeom<false> {  // minutiae: <= 120 candidates
-    static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 3072, NCH = 4;
+    static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 2560, NCH = 4;
 };
 template <>
 struct SparseGeom<true> {  // texture: <= 200 candidates
-    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 4608, NCH = 7;
+    static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 4352, NCH = 7;
 };
 
 // Working set of one job.  The graph is built symmetrically: only the pairs a < b are tested, a bit matrix M records
@@ -48,15 +48,15 @@ struct SparseWork {
     static constexpr int P2 = G::MAXP <= 128 ? 128 : 256;
     float vals[G::CAP];            // CSR values; before the graph is built the texture kernel sorts row maxima here
     float4 cf[G::MAXP];            // candidate coordinates as floats (exact): latent x, rolled x, latent y, rolled y
-    uint32_t M[G::MAXP][G::NCH];   // bit matrix of possibly connected pairs
     float v[G::MAXP];
     float lo[G::MAXP], ro[G::MAXP];
     unsigned short li[G::MAXP], rj[G::MAXP];
     unsigned short row_start[P2], row_len[G::MAXP];
     unsigned char cols[G::CAP];
     unsigned short up_pos[P2];     // first CSR slot right of the diagonal of every row
-    union {
-        unsigned short up_start[P2 + 1];   // prefix sums of the rows' counts of pairs a < b: dead once the CSR is built
+    unsigned short up_start[P2];   // prefix sums of the rows' counts of pairs a < b
+    union {                        // the bit matrix is dead once the CSR is built: its storage becomes the iteration vectors
+        uint32_t M[G::MAXP][G::NCH];       // bit matrix of possibly connected pairs
         struct {
             float b[G::MAXP], c[G::MAXP];
             unsigned short y[G::MAXP];     // candidates in std::sort order
@@ -194,11 +194,11 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
                     if (lane == c) keep = m;
                 }
                 if (lane == r) keep &= ~kbit;                      // not with itself
-                if (lane >= r && lane < NCH) w.M[i][lane] = keep;  // the row's own chunk and everything right of it
+                if (lane >= r && lane < NCH) w.u.M[i][lane] = keep;  // the row's own chunk and everything right of it
             }
 #pragma unroll
             for (int c = r + 1; c < NCH; ++c)
-                if (tacc[c]) atomicOr(&w.M[32 * c + lane][r], tacc[c]);
+                if (tacc[c]) atomicOr(&w.u.M[32 * c + lane][r], tacc[c]);
         }
     }
     __syncthreads();
@@ -210,7 +210,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             const uint32_t above = (k == 31) ? 0u : ~((2u << k) - 1u);
 #pragma unroll
             for (int c = 0; c < G::NCH; ++c) {
-                const uint32_t word = w.M[tid][c];
+                const uint32_t word = w.u.M[tid][c];
                 len += __popc(word);
                 up += __popc(c > r ? word : (c == r ? (word & above) : 0u));
             }
@@ -232,7 +232,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             w.row_start[tid] = (unsigned short)(excl & 0xffff);
             w.up_pos[tid] = (unsigned short)((excl & 0xffff) + len - up);  // first CSR slot right of the diagonal
             if (tid < num) w.row_len[tid] = (unsigned short)len;
-            w.u.up_start[tid] = tid < num ? (unsigned short)(excl >> 16) : (unsigned short)0xffffu;
+            w.up_start[tid] = tid < num ? (unsigned short)(excl >> 16) : (unsigned short)0xffffu;
         }
         if (tid == NT - 1) {
             w.npairs = (before + inc) >> 16;
@@ -251,8 +251,8 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             int a = 0;
 #pragma unroll
             for (int step = P2 / 2; step >= 1; step >>= 1)
-                if (w.u.up_start[a + step] <= e) a += step;
-            const int k0 = e - w.u.up_start[a];
+                if (w.up_start[a + step] <= e) a += step;
+            const int k0 = e - w.up_start[a];
             const int r = a >> 5, ka = a & 31;
             const uint32_t above = (ka == 31) ? 0u : ~((2u << ka) - 1u);
             int k = k0, cw = 0;
@@ -260,7 +260,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             bool found = false;
 #pragma unroll
             for (int c = 0; c < G::NCH; ++c) {
-                const uint32_t x0 = w.M[a][c];
+                const uint32_t x0 = w.u.M[a][c];
                 const uint32_t x = c > r ? x0 : (c == r ? (x0 & above) : 0u);
                 const int cnt = __popc(x);
                 const bool here = !found & (k < cnt);
@@ -283,14 +283,14 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             const int b = 32 * cw + pos;
             const float h = pair_h<LOOKUP>(w.cf[a], w.cf[b], table);
             const int pa = w.up_pos[a] + k0;
-            const int pb = w.row_start[b] + bits_below<G::NCH>(w.M[b], a);
+            const int pb = w.row_start[b] + bits_below<G::NCH>(w.u.M[b], a);
             w.vals[pa] = h;
             w.cols[pa] = (unsigned char)b;
             w.vals[pb] = h;
             w.cols[pb] = (unsigned char)a;
         }
     }
-    __syncthreads();  // the prefix sums are dead: their storage becomes the iteration vectors
+    __syncthreads();  // the bit matrix is dead: its storage becomes the iteration vectors
     if (tid < num) w.u.it.b[tid] = w.v[tid];
     __syncthreads();
 
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         w.tie = 0;
         w.npairs = 0;
     }
-    for (int e = tid; e < SparseGeom<false>::MAXP * SparseGeom<false>::NCH; e += SparseGeom<false>::NT) (&w.M[0][0])[e] = 0u;
+    for (int e = tid; e < SparseGeom<false>::MAXP * SparseGeom<false>::NCH; e += SparseGeom<false>::NT) (&w.u.M[0][0])[e] = 0u;
     int big = 0;
     if (tid < num) {
         const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
         w.tie = 0;
         w.npairs = 0;
     }
-    for (int e = tid; e < SparseGeom<true>::MAXP * SparseGeom<true>::NCH; e += NT) (&w.M[0][0])[e] = 0u;
+    for (int e = tid; e < SparseGeom<true>::MAXP * SparseGeom<true>::NCH; e += NT) (&w.u.M[0][0])[e] = 0u;
     const size_t rbase = pair * (size_t)P.lt_stride;
     int num;
     if (nLt > kTopCorrTex) {

@@ -466,7 +466,9 @@ int lafis_gallery_load_files(lafis_ctx* c, const char* const* paths, int n, int 
     });
     unsigned long long pool_cap = 0;
     for (unsigned long long b : part_bytes) pool_cap += b;
-    constexpr size_t kSlotBytes = (size_t)8 << 20;  // > the largest template (2000 minutiae + 2000 texture points: 0.9 MB)
+    // staging slots: 1/8 of a thread's share, between 1 MB (> the largest template: 2000 minutiae + 1000 texture points
+    // = 0.8 MB) and 8 MB - pinning memory costs time too, and a 2,000-file gallery should not pin 400 MB for it
+    const size_t kSlotBytes = std::min<size_t>((size_t)8 << 20, std::max<size_t>((size_t)1 << 20, (size_t)(pool_cap / n_threads / 8 + 0xfffff) & ~(size_t)0xfffff));
     constexpr int kRing = 3;
     unsigned char* d_pool = nullptr;
     LAFIS_CUDA(c, cudaMalloc(&d_pool, std::max<unsigned long long>(pool_cap, 16)));
@@ -1076,7 +1078,8 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     // where one chain's kernels fill the tails of the other's; with a single chunk every kernel is issue-bound on
     // its own and the overlap only adds contention (measured: 87.3 against 88.3 ms for 1 latent x 100,000 prints in
     // one chunk, 2,357 against 2,375 ms for 27 latents in ten chunks).
-    const bool two = c->two_streams && n_chunks > 1;
+    static const bool force_two = getenv("LAFIS_FORCE_TWO_STREAMS") != nullptr;  // experiment switch
+    const bool two = c->two_streams && (n_chunks > 1 || force_two);
     cudaStream_t sb = two ? c->stream_b : st;
     auto begin = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage], s_); };
     auto end = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage + 1], s_); };
@@ -1220,14 +1223,15 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.g0 = g0;
             P.n_chunk = n_chunk;
             const int n_rowtiles = L->lt_stride / kRowTile;
-            // Jobs (row tile x slice of the chunk) are drawn dynamically by one persistent CTA per SM.  With as many
-            // slices as SMs the number of equal-sized jobs is a multiple of the grid, so no CTA runs a lone extra
-            // job while the others idle (a 4.04-jobs-per-CTA split used to cost 20 % of this kernel); small chunks
-            // are cut into >= 64-template slices until there are ~4 jobs per SM.
-            int slices;
-            if (n_chunk >= 128 * c->sm_count) {
-                slices = c->sm_count;
-            } else {
+            // Jobs = (slice of the chunk, latent, row tile), drawn dynamically and slice-major by one persistent CTA per SM.
+            // Slices of ~352 templates (~4.5 MB of code words): the few slices in flight at any time stay in L2, so the
+            // gallery's code words come from HBM about once per launch, whatever the number of row tiles and latents.
+            // With at least one slice per SM the count is rounded to a multiple of the SM count, so that the number of
+            // (equal-sized) jobs is a multiple of the grid; chunks too small for ~4 jobs per SM are cut into slices of
+            // >= 64 templates.
+            int slices = std::max(1, n_chunk / 352);
+            if (slices >= c->sm_count) slices = (slices + c->sm_count / 2) / c->sm_count * c->sm_count;
+            if ((long long)slices * Q * n_rowtiles < 4ll * c->sm_count) {
                 slices = (4 * c->sm_count + Q * n_rowtiles - 1) / (Q * n_rowtiles);
                 slices = std::max(1, std::min(slices, (n_chunk + 63) / 64));
             }

@@ -206,9 +206,13 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
         __syncthreads();
         const int job = s_job;
         if (job >= n_jobs) break;
-        const int slice = job % P.slices;
-        const int rt = (job / P.slices) % n_rowtiles;
-        const int q = job / (P.slices * n_rowtiles);
+        // slice-major job order: the (latent, row tile) jobs of one gallery slice are drawn back to back, so the CTAs
+        // working at any time share a handful of slices whose code words stay in L2 - the gallery is read from HBM
+        // about once per launch instead of once per row tile and latent
+        const int per_slice = P.Q * n_rowtiles;
+        const int slice = job / per_slice;
+        const int q = (job - slice * per_slice) / n_rowtiles;
+        const int rt = job - slice * per_slice - q * n_rowtiles;
         const int nLt = P.lat_nt[q];
         if (rt * kRowTile >= nLt) continue;  // uniform across the CTA
 

@@ -17,14 +17,21 @@ from .matcher import Matcher, PackedGallery, pack_rolled
 # not - minutiae concentrated in the central ridge area (denser distance-consistency graphs), descriptors drawn from
 # a few directions per print plus noise (correlated similarity rows; many PQ columns near each row minimum), and
 # near-duplicates of the probes' mates in the gallery (mated-like dense graphs).
-HARD_SIGMA_PX = 110.0      # std of the minutiae cloud around the image centre
-HARD_CENTRES = 12          # descriptor directions per print
-HARD_NOISE = 0.45          # descriptor = normalise(centre + HARD_NOISE * unit noise) * 1.73
-HARD_DUP_FRACTION = 0.01   # share of the gallery that is a jittered copy of a head template
+HARD = {  # profile name -> (std of the minutiae cloud [px], descriptor directions per print, noise, near-duplicate share)
+    "hard": (110.0, 12, 0.45, 0.01),
+    "harder": (60.0, 4, 0.25, 0.05),
+}
+HARD_SIGMA_PX, HARD_CENTRES, HARD_NOISE, HARD_DUP_FRACTION = HARD["hard"]
 
 
-def harden_raw(raw: T.RolledRaw, seed: int) -> T.RolledRaw:
+def _use_profile(profile: str):
+    global HARD_SIGMA_PX, HARD_CENTRES, HARD_NOISE, HARD_DUP_FRACTION
+    HARD_SIGMA_PX, HARD_CENTRES, HARD_NOISE, HARD_DUP_FRACTION = HARD.get(profile, HARD["hard"])
+
+
+def harden_raw(raw: T.RolledRaw, seed: int, profile: str = "hard") -> T.RolledRaw:
     """Host-side version of the hard profile for the head templates (the probes' mates)."""
+    _use_profile(profile)
     rng = np.random.default_rng(77000 + seed)
     m = raw.minu
     n = m.n
@@ -45,7 +52,8 @@ def synth_gallery_device(m: Matcher, n: int, seed: int, head: Sequence[T.FPTempl
     n - len(head) templates drawn on the device.  Must be called with the matcher's stream current
     (`torch.cuda.stream(torch.cuda.ExternalStream(m.stream))`).  profile "hard": see HARD_* above."""
     import torch
-    hard = profile == "hard"
+    hard = profile in HARD
+    _use_profile(profile)
 
     dev = device if device is not None else torch.device("cuda", m.device)
     g = torch.Generator(device=dev)

@@ -229,7 +229,7 @@ def test_oversized_templates_across_pipeline_chunks(pkg, built, golden, oracle, 
     assert st["minu_big_jobs"] == 3 * 9 + 3 * 3   # the oversized latent against everything + the other against 3 templates
 
 
-def test_texture_score_in_an_unweighted_slot(pkg, matcher, golden, oracle):
+def test_texture_score_in_an_unweighted_slot(pkg, built, golden, oracle):
     """Latents with 1 or 2 minutiae templates: the reference stores the texture score in score[1], score[2] (matcher.cpp:414)
     and fuses it with weight 1 (:188); with 5 minutiae templates it is never read.  Library vs oracle, bit for bit."""
     from test_oracle_vs_reference import _odd_layout_latents
@@ -238,10 +238,13 @@ def test_texture_score_in_an_unweighted_slot(pkg, matcher, golden, oracle):
     raws = [T.synth_rolled_raw(4100 + g, n_minu=50, n_tex=150) for g in range(3)]
     rolled = [T.rolled_from_raw(r, cb) for r in raws]
     latents = _odd_layout_latents(T, raws)
+    matcher = pkg.Matcher(codebook=cb, device=0)
     matcher.set_gallery(pkg.pack_rolled(rolled))
     L = matcher.latents_from_packed(pkg.pack_latents(latents))
     assert [L.status(q) for q in range(3)] == [0, 0, 0]
     out = matcher.match(L, topk=2, want_components=True)
+    L.free()
+    matcher.close()
     rc, comp, fin = oracle_scores(oracle, T, latents, rolled, cb)
     assert (rc == 0).all()
     assert np.array_equal(out["components"], comp), (out["components"], comp)

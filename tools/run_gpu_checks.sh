@@ -1,15 +1,23 @@
 #!/bin/bash
-# Dev helper for one gpurun call: GPU tests, the benchmark (i.i.d. and hard profile), ingest at 100,000 directory
-# entries and an ncu capture of the selection kernel.  usage: tools/run_gpu_checks.sh <tag>
-tag=${1:-x}
+# Dev helper for one gpurun call.  usage: tools/run_gpu_checks.sh <tag> [steps...]
+# steps: tests bench hard harder ingest ncu_all launches sub
+tag=${1:-x}; shift
 out=gpurun_out
-python -m pytest tests -m gpu -x -q > $out/${tag}_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -3 $out/${tag}_gpu_tests.log
-python bench.py --no-sub > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
-python bench.py --no-sub --profile hard > $out/${tag}_bench_hard.json 2> $out/${tag}_bench_hard.err; echo "hard rc=$?"; tail -c 400 $out/${tag}_bench_hard.err
-python tools/bench_ingest.py 2000 100000 > $out/${tag}_ingest.json 2> $out/${tag}_ingest.err; echo "ingest rc=$?"; tail -c 300 $out/${tag}_ingest.err; cat $out/${tag}_ingest.json
+for step in "$@"; do
+case $step in
+tests) python -m pytest tests -m gpu -x -q > $out/${tag}_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -3 $out/${tag}_gpu_tests.log;;
+bench) python bench.py --no-sub > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?";;
+sub) python bench.py > $out/${tag}_bench_full.json 2> $out/${tag}_bench_full.err; echo "bench full rc=$?";;
+hard) python bench.py --no-sub --profile hard > $out/${tag}_bench_hard.json 2> $out/${tag}_bench_hard.err; echo "hard rc=$?";;
+harder) python bench.py --no-sub --profile harder > $out/${tag}_bench_harder.json 2> $out/${tag}_bench_harder.err; echo "harder rc=$?"; tail -c 300 $out/${tag}_bench_harder.err;;
+ingest) python tools/bench_ingest.py 2000 100000 > $out/${tag}_ingest.json 2> $out/${tag}_ingest.err; echo "ingest rc=$?"; tail -c 300 $out/${tag}_ingest.err; cat $out/${tag}_ingest.json;;
+ncu_all) ncu --set full --clock-control none --import-source on -k regex:"tex_rowmax|minu_sim_kernel|minu_select_kernel|graph_minu_sparse|graph_tex_sparse" -s 5 -c 5 -o $out/prof_${tag}_all -f python bench.py --steps 1 --warmup 1 --no-sub --parity-sample 64 > $out/ncu_${tag}.log 2>&1; tail -2 $out/ncu_${tag}.log;;
+launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}.csv python bench.py --steps 2 --warmup 1 --no-sub --parity-sample 64 > $out/launches_${tag}.log 2>&1; tail -1 $out/launches_${tag}.log | cut -c1-200;;
+esac
+done
 python - <<PY
-import json
-for f in ("$out/${tag}_bench.json","$out/${tag}_bench_hard.json"):
+import json, glob
+for f in sorted(glob.glob("$out/${tag}_bench*.json")):
     try:
         d=json.loads(open(f).read().strip().split("\n")[-1])
         print(f, d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["parity"], d["exactness"])
@@ -17,4 +25,3 @@ for f in ("$out/${tag}_bench.json","$out/${tag}_bench_hard.json"):
     except Exception as e:
         print(f, "unreadable", e)
 PY
-ncu --set full --clock-control none --import-source on -k regex:"minu_select_kernel" -s 1 -c 1 -o $out/prof_${tag}_select -f python bench.py --steps 1 --warmup 1 --no-sub --parity-sample 64 > $out/ncu_${tag}.log 2>&1; tail -2 $out/ncu_${tag}.log
