@@ -33,7 +33,8 @@
 
 namespace lafis {
 
-constexpr int kSimThreads = 512;
+constexpr int kSimThreads = 384;   // 12 warps: the 3 x 80 latent rows make 12 tiles of 20 rows, 3 per scheduler
+constexpr int kSimTileRows = 20;   // rows of a warp tile (10 per thread, two thread rows)
 constexpr int kSelThreads = 384;  // 12 warps per job, 4 jobs per SM (shared memory): 48 of 64 warp slots
 constexpr uint32_t kSelBinBase = (127u - 16u) << 6;
 
@@ -70,30 +71,37 @@ struct MinuSimParams {
 };
 
 
-// One warp tile of S = max(0, A.B^T): rows i0..i0+7 of this thread (16 per warp) and NC columns per thread,
-// 16 lanes across: NC = 8 is the 128-column tile (columns jbase + {lj*4..+3, 64+lj*4..+3}); the other widths
-// (96, 112, 144, 160 columns for NC = 6, 7, 9, 10) let one tile span a whole template with at most 15 padding
-// columns: 4 @ lj*4, then 4 @ 64+lj*4 (NC >= 8) or 2 @ 64+lj*2 (NC < 8), then the remaining 1 or 2 columns.
-// k ascending, unfused.
+// One warp tile of S = max(0, A.B^T): 20 rows x 16*NC columns.  A thread owns 10 rows - 8 consecutive ones at
+// tile + li*8 and 2 at tile + 16 + li*2 (li = lane / 16), so that its A operands are two 16-byte and one 8-byte shared
+// memory load per k - and NC columns, 16 lanes across: NC = 8 is the 128-column tile (columns jbase + {lj*4..+3,
+// 64+lj*4..+3}); the other widths (96, 112, 144, 160 columns for NC = 6, 7, 9, 10) let one tile span a whole template
+// with at most 15 padding columns: 4 @ lj*4, then 4 @ 64+lj*4 (NC >= 8) or 2 @ 64+lj*2 (NC < 8), then the remaining 1
+// or 2 columns.  k ascending, unfused.  With 3 x 80 latent rows the 12 tiles keep all 12 warps (3 per scheduler)
+// equally busy; the former 16-row tiles left one of 16 warps idle and one scheduler a quarter short.
 template <int NC>
-__device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, const float* __restrict__ Bt, int npR, int lj,
-                                         int jbase, int i0, int nL, float* __restrict__ out) {
+__device__ __forceinline__ void sim_tile(const float* __restrict__ As, int tile0, int li, int npL, const float* __restrict__ Bt,
+                                         int npR, int lj, int jbase, int nL, float* __restrict__ out) {
     constexpr int N2 = NC >= 8 ? 4 : 2;          // width of the second column group
     constexpr int N3 = NC - 4 - N2;              // width of the third (0, 1 or 2)
     constexpr int J3 = 64 + 16 * N2;             // its first column: 128 or 96
+    constexpr int RT = 10;
     const int ja = jbase + lj * 4, jb = jbase + 64 + lj * N2, jc = jbase + J3 + lj * N3;
     const float* bpa = Bt + ja;
     const float* bpb = Bt + jb;
     const float* bpc = Bt + jc;
-    float acc[8][NC];
+    const int i8 = tile0 + li * 8, i2 = tile0 + 16 + li * 2;
+    const float* ap8 = As + i8;
+    const float* ap2 = As + i2;
+    float acc[RT][NC];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < RT; ++a)
 #pragma unroll
         for (int b = 0; b < NC; ++b) acc[a][b] = 0.0f;
 #pragma unroll 2
     for (int k = 0; k < 96; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(ap + k * npL);
-        const float4 a1 = *reinterpret_cast<const float4*>(ap + k * npL + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(ap8 + k * npL);
+        const float4 a1 = *reinterpret_cast<const float4*>(ap8 + k * npL + 4);
+        const float2 a2 = *reinterpret_cast<const float2*>(ap2 + k * npL);
         float bv[NC];
         {
             const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
@@ -112,15 +120,15 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ ap, int npL, 
         } else if (N3 == 1) {
             bv[NC - 1] = bpc[k * npR];
         }
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float av[RT] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < RT; ++a)
 #pragma unroll
             for (int b = 0; b < NC; ++b) acc[a][b] = f_add(acc[a][b], f_mul(av[a], bv[b]));
     }
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int i = i0 + a;
+    for (int a = 0; a < RT; ++a) {
+        const int i = a < 8 ? i8 + a : i2 + (a - 8);
         if (i >= nL) continue;
         float v[NC];
 #pragma unroll
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
                 const int rows = P.slot_n[q * 3 + s] <= P.l_cap ? P.slot_n[q * 3 + s] : 0;
-                t0[s + 1] = t0[s] + ((rows + 15) >> 4) * tiles_jj;
+                t0[s + 1] = t0[s] + ((rows + kSimTileRows - 1) / kSimTileRows) * tiles_jj;
             }
             for (int t = warp; t < t0[3]; t += NW) {
                 const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
@@ -221,15 +229,14 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
                 const int ti = tt / tiles_jj, tj = tt - ti * tiles_jj;
                 const int nL = P.slot_n[q * 3 + s];
                 const int npL = (nL + 3) & ~3;
-                const int i0 = ti * 16 + li * 8;
-                const float* ap = A + (size_t)s * P.a_slot_stride + i0;
+                const float* As = A + (size_t)s * P.a_slot_stride;
                 float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
                 switch (nc) {
-                    case 6: sim_tile<6>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                    case 7: sim_tile<7>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                    case 9: sim_tile<9>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                    case 10: sim_tile<10>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                    default: sim_tile<8>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out); break;
+                    case 6: sim_tile<6>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                    case 7: sim_tile<7>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                    case 9: sim_tile<9>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                    case 10: sim_tile<10>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                    default: sim_tile<8>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, tj * 128, nL, out); break;
                 }
             }
         }
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
                     const int rows = P.slot_n[q * 3 + s] <= P.l_cap ? P.slot_n[q * 3 + s] : 0;
-                    t0[s + 1] = t0[s] + ((rows + 15) >> 4) * tiles_jj;
+                    t0[s + 1] = t0[s] + ((rows + kSimTileRows - 1) / kSimTileRows) * tiles_jj;
                 }
                 for (int t = warp; t < t0[3]; t += NW) {
                     const int s = (t >= t0[2]) ? 2 : (t >= t0[1]) ? 1 : 0;
@@ -324,15 +331,14 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_jobs_kernel(MinuSimPa
                     const int ti = tt / tiles_jj, tj = tt - ti * tiles_jj;
                     const int nL = P.slot_n[q * 3 + s];
                     const int npL = (nL + 3) & ~3;
-                    const int i0 = ti * 16 + li * 8;
-                    const float* ap = A + (size_t)s * P.a_slot_stride + i0;
+                    const float* As = A + (size_t)s * P.a_slot_stride;
                     float* out = P.S + ((size_t)((size_t)q * P.n_chunk + tl) * 3 + s) * P.job_stride;
                     switch (nc) {
-                        case 6: sim_tile<6>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                        case 7: sim_tile<7>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                        case 9: sim_tile<9>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                        case 10: sim_tile<10>(ap, npL, Bt, npR, lj, 0, i0, nL, out); break;
-                        default: sim_tile<8>(ap, npL, Bt, npR, lj, tj * 128, i0, nL, out); break;
+                        case 6: sim_tile<6>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                        case 7: sim_tile<7>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                        case 9: sim_tile<9>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                        case 10: sim_tile<10>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, 0, nL, out); break;
+                        default: sim_tile<8>(As, ti * kSimTileRows, li, npL, Bt, npR, lj, tj * 128, nL, out); break;
                     }
                 }
             }
