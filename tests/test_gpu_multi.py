@@ -251,3 +251,23 @@ def test_one_process_per_gpu_comm_init(pkg, matcher, golden, tmp_path):
     import json
     info = json.loads(outs[0][0].strip().split("\n")[-1])
     assert info["total"] == 29 and info["base"] == [0, 14] and info["n"] == [14, 15] and info["world"] == 2
+
+
+@need2
+def test_group_over_all_visible_gpus(pkg, matcher, golden, tmp_path):
+    """MatcherGroup over every visible device (8 on the scaling box): rank lists and score rows equal the single-GPU
+    matcher's, with shards of unequal size and, when there are more devices than a multiple allows, tiny shards."""
+    cb = golden["codebook"]
+    T = pkg.templates
+    cbp = os.path.join(str(tmp_path), "cb.dat")
+    T.write_codebook(cbp, cb)
+    n_dev = n_gpus()
+    rolled, latents = _synthetic_set(pkg, cb, n=3 * n_dev + 5, seed=2100)
+    gdir, ldir, gp, lp = _write_files(pkg, rolled, latents[:2], str(tmp_path))
+    matcher.load_gallery_files(gp)
+    one = matcher.match(matcher.load_latents(lp), topk=10)
+    grp = pkg.MatcherGroup(cbp, list(range(n_dev)))
+    assert grp.load_gallery_files(gp) == len(gp)
+    two = grp.match(grp.load_latents(lp), topk=10)
+    assert np.array_equal(one["scores"], two["scores"]) and np.array_equal(one["hits"], two["hits"])
+    grp.close()
