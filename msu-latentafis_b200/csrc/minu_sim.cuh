@@ -156,12 +156,20 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
     constexpr int NW = kSimThreads / 32;
     const int li = lane >> 4, lj = lane & 15;
 
-    auto load_B = [&](int tl, int buf) {
-        const int g = P.g0 + tl;
-        const int nR = P.minu_n[g];
+    // a template's size and offset are read one step before they are needed (two templates ahead of the one being
+    // multiplied): the global-load latency of these two words would otherwise stall the whole CTA once per template
+    auto head = [&](int tl, int& nR, uint32_t& off) {
+        nR = 0;
+        off = 0;
+        if (tl < P.n_chunk) {
+            nR = P.minu_n[P.g0 + tl];
+            off = P.minu_off[P.g0 + tl];
+        }
+    };
+    auto load_B = [&](int nR, uint32_t off, int buf) {
         if (nR <= 0 || nR > P.r_cap) return;
         const int np = (nR + 3) & ~3;
-        const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * P.minu_off[g]);
+        const float4* src = reinterpret_cast<const float4*>(P.minu_desT + (size_t)96 * off);
         float4* dst = reinterpret_cast<float4*>(B + (size_t)buf * P.b_buf_stride);
         for (int e = tid; e < 24 * np; e += kSimThreads) cp_async16(dst + e, src + e);
     };
@@ -178,21 +186,24 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
 
     int tl = blockIdx.x;
     if (tl >= P.n_chunk) return;
-    load_B(tl, 0);
+    int nR, nR_next, nR_next2;
+    uint32_t off, off_next, off_next2;
+    head(tl, nR, off);
+    head(tl + gridDim.x, nR_next, off_next);
+    load_B(nR, off, 0);
     if (P.Q == 1) load_A(0);
     cp_async_commit();
 
     for (int it = 0; tl < P.n_chunk; tl += gridDim.x, ++it) {
         const int cur = P.b_double ? (it & 1) : 0;
         const int tl_next = tl + gridDim.x;
+        head(tl_next + gridDim.x, nR_next2, off_next2);  // consumed in the next iteration
         bool prefetched = false;
         if (P.b_double && tl_next < P.n_chunk) {
-            load_B(tl_next, cur ^ 1);
+            load_B(nR_next, off_next, cur ^ 1);
             prefetched = true;
         }
         cp_async_commit();
-        const int g = P.g0 + tl;
-        const int nR = P.minu_n[g];
         const int npR = (nR + 3) & ~3;
         const float* Bt = B + (size_t)cur * P.b_buf_stride;
         const int tiles_j = (nR + 127) >> 7;
@@ -242,9 +253,13 @@ __global__ void __launch_bounds__(kSimThreads, 1) minu_sim_kernel(MinuSimParams 
         }
         __syncthreads();  // everyone is done with this gallery block before it is overwritten
         if (!P.b_double && tl_next < P.n_chunk) {
-            load_B(tl_next, 0);
+            load_B(nR_next, off_next, 0);
             cp_async_commit();
         }
+        nR = nR_next;
+        off = off_next;
+        nR_next = nR_next2;
+        off_next = off_next2;
     }
     cp_async_wait<0>();
 }
