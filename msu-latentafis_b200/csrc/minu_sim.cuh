@@ -90,8 +90,9 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ As, int tile0
     const float* bpb = Bt + jb;
     const float* bpc = Bt + jc;
     const int i8 = tile0 + li * 8, i2 = tile0 + 16 + li * 2;
-    const float* ap8 = As + i8;
-    const float* ap2 = As + i2;
+    // operand pointers advance by one k-row per step (one add each instead of a multiply-add per load)
+    const float* pa8 = As + i8;
+    const float* pa2 = As + i2;
     float acc[RT][NC];
 #pragma unroll
     for (int a = 0; a < RT; ++a)
@@ -99,27 +100,33 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ As, int tile0
         for (int b = 0; b < NC; ++b) acc[a][b] = 0.0f;
 #pragma unroll 2
     for (int k = 0; k < 96; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(ap8 + k * npL);
-        const float4 a1 = *reinterpret_cast<const float4*>(ap8 + k * npL + 4);
-        const float2 a2 = *reinterpret_cast<const float2*>(ap2 + k * npL);
+        const float4 a0 = *reinterpret_cast<const float4*>(pa8);
+        const float4 a1 = *reinterpret_cast<const float4*>(pa8 + 4);
+        const float2 a2 = *reinterpret_cast<const float2*>(pa2);
+        pa8 += npL;
+        pa2 += npL;
         float bv[NC];
         {
-            const float4 b0 = *reinterpret_cast<const float4*>(bpa + k * npR);
+            const float4 b0 = *reinterpret_cast<const float4*>(bpa);
             bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
         }
         if (N2 == 4) {
-            const float4 b1 = *reinterpret_cast<const float4*>(bpb + k * npR);
+            const float4 b1 = *reinterpret_cast<const float4*>(bpa + 64);  // jb = ja + 64
             bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
         } else {
-            const float2 b1 = *reinterpret_cast<const float2*>(bpb + k * npR);
+            const float2 b1 = *reinterpret_cast<const float2*>(bpb);
             bv[4] = b1.x, bv[5] = b1.y;
+            bpb += npR;
         }
         if (N3 == 2) {
-            const float2 b2 = *reinterpret_cast<const float2*>(bpc + k * npR);
+            const float2 b2 = *reinterpret_cast<const float2*>(bpc);
             bv[NC - 2] = b2.x, bv[NC - 1] = b2.y;
+            bpc += npR;
         } else if (N3 == 1) {
-            bv[NC - 1] = bpc[k * npR];
+            bv[NC - 1] = *bpc;
+            bpc += npR;
         }
+        bpa += npR;
         const float av[RT] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
 #pragma unroll
         for (int a = 0; a < RT; ++a)
