@@ -15,16 +15,22 @@
 namespace lafis {
 
 constexpr int kMaxDynSmem = 227 * 1024 - 1024;  // kernels also hold a little static shared memory
-constexpr int kSelMaxCand = 512;  // sorted in the histogram's 4 KB (512 x 8 B)
+constexpr int kSelMaxCand = 512;  // indices + keys in the histogram's 4 KB (2 x 512 x 4 B)
 constexpr int kSelBins = 1024;  // 64 bins per binade over [2^-16, 1): float bits >> 17, offset; smaller values share bin 0
 
 LAFIS_PLAN_HD inline size_t minu_sim_smem_bytes(int a_slot_stride, int b_buf_stride, int b_double) {
     return sizeof(float) * ((size_t)3 * a_slot_stride + (size_t)(b_double ? 2 : 1) * b_buf_stride);
 }
 
+// Row stride (floats) of minu_select_kernel's copy of a similarity matrix with np (a multiple of 4) padded columns:
+// the next multiple of 4 that is 4 mod 8 - rows stay 16-byte aligned and eight consecutive rows start in eight different
+// 16-byte bank groups.
+LAFIS_PLAN_HD inline int sel_ld(int np) { return (np & 4) ? np : np + 4; }
+
+// the copy of S, row and column sums, and 4 KB that hold the 1024-bin histogram first and the candidate list
+// (kSelMaxCand indices + kSelMaxCand keys) afterwards
 LAFIS_PLAN_HD inline size_t minu_select_smem_bytes(int max_nL, int max_np) {
-    return sizeof(float) * ((size_t)max_nL * (max_np + 1) + max_nL + max_np) + sizeof(int) * kSelBins +
-           sizeof(int) * kSelMaxCand + 16;
+    return sizeof(float) * ((size_t)max_nL * sel_ld(max_np) + ((max_nL + 3) & ~3) + max_np) + sizeof(int) * kSelBins + 16;
 }
 
 LAFIS_PLAN_HD inline size_t minu_select_slow_smem_bytes(int max_nL, int max_np, bool dense) {

@@ -411,10 +411,15 @@ __device__ __forceinline__ float approx_key(float s, float l, float r) {
     return s * rc;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(x));  // 1 ulp
+    return rc;
+}
+
 __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kSelThreads / 32;
     const size_t job = blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
     const int slot = (int)(job % 3);
     const size_t pair = job / 3;
@@ -426,55 +431,40 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
         if (tid == 0) P.corr_n[job] = 0;
         return;
     }
-    const int np = (nR + 3) & ~3, ld = np + 1;
+    const int np = (nR + 3) & ~3, G = np >> 2, ld = sel_ld(np);
     float* Ssm = reinterpret_cast<float*>(smem);                       // [nL][ld]
-    float* lsum = Ssm + (size_t)P.max_nL * (P.max_np + 1);             // [nL]
-    float* rsum = lsum + P.max_nL;                                     // [nR]
-    int* hist = reinterpret_cast<int*>(rsum + P.max_np);               // [1024]
-    int* cand_e = reinterpret_cast<int*>(hist + kSelBins);             // [kSelMaxCand]
-    __shared__ int s_ncand, s_npos, s_flag, s_bin;
+    float* lsum = Ssm + (size_t)P.max_nL * sel_ld(P.max_np);           // [nL]
+    float* rsum = lsum + ((P.max_nL + 3) & ~3);                        // [np], 16-byte aligned
+    int* hist = reinterpret_cast<int*>(rsum + P.max_np);               // [1024]; later: candidates and their keys
+    uint32_t* cand_ij = reinterpret_cast<uint32_t*>(hist);             // [kSelMaxCand] (i << 16) | j
+    uint32_t* cand_key = cand_ij + kSelMaxCand;                        // [kSelMaxCand] exact keys
+    __shared__ int s_ncand, s_bad;
     __shared__ float s_thr;
-    __shared__ int s_order[kTopCorrMinu];
+    __shared__ unsigned char s_slot[kTopCorrMinu + 8];
+
+    // a thread owns one group of four consecutive columns (g) and every RP-th row: its four column sums stay in
+    // registers through both passes, and every access to the copy of S is a 16-byte one
+    const int RP = kSelThreads / G;  // rows in flight (G <= 90: r_cap <= 360)
+    const int g = tid % G, r0 = tid / G;
+    const bool active = r0 < RP;
 
     const float* Sg = P.S + job * P.job_stride;
-    {   // a warp copies two rows at a time with coalesced 4-byte loads: consecutive lanes then also store to
-        // consecutive banks of the odd-stride copy (16-byte loads needed four 4-way conflicting stores each)
-        for (int i = warp; i < nL; i += 2 * NW) {
-            const float* r0 = Sg + (size_t)i * np;
-            const float* r1 = Sg + (size_t)(i + NW) * np;
-            const bool has1 = i + NW < nL;
-            float v0[5], v1[5];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int j = lane + 32 * k;
-                v0[k] = j < np ? __ldcs(r0 + j) : 0.0f;
-                v1[k] = (has1 && j < np) ? __ldcs(r1 + j) : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int j = lane + 32 * k;
-                if (j < np) {
-                    Ssm[i * ld + j] = v0[k];
-                    if (has1) Ssm[(i + NW) * ld + j] = v1[k];
-                }
-            }
-            for (int j = lane + 160; j < np; j += 32) {  // templates beyond 160 minutiae
-                Ssm[i * ld + j] = __ldcs(r0 + j);
-                if (has1) Ssm[(i + NW) * ld + j] = __ldcs(r1 + j);
-            }
-        }
-    }
+    if (active)
+        for (int i = r0; i < nL; i += RP) cp_async16(Ssm + i * ld + 4 * g, Sg + (size_t)i * np + 4 * g);
+    cp_async_commit();
     for (int b = tid; b < kSelBins; b += kSelThreads) hist[b] = 0;
+    if (tid < kTopCorrMinu + 8) s_slot[tid] = 0;
     if (tid == 0) {
         s_ncand = 0;
-        s_npos = 0;
-        s_flag = 0;
+        s_bad = 0;
     }
+    cp_async_wait<0>();
     __syncthreads();
 
-    // ---- K6: sums.  first half of the CTA: columns (i ascending); second half: rows (j ascending) ----
+    // ---- K6: sums.  first half of the CTA: columns (i ascending); second half: rows (j ascending; the padding
+    //      columns hold +0, which leaves a non-negative fp32 accumulator unchanged) ----
     if (tid < kSelThreads / 2) {
-        for (int j = tid; j < nR; j += kSelThreads / 2) {
+        for (int j = tid; j < np; j += kSelThreads / 2) {
             float acc = Ssm[j];
 #pragma unroll 8
             for (int i = 1; i < nL; ++i) acc = f_add(acc, Ssm[i * ld + j]);
@@ -482,50 +472,64 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
         }
     } else {
         for (int i = tid - kSelThreads / 2; i < nL; i += kSelThreads / 2) {
-            const float* row = Ssm + i * ld;
-            float acc = row[0];
-#pragma unroll 8
-            for (int j = 1; j < nR; ++j) acc = f_add(acc, row[j]);
+            const float4* row = reinterpret_cast<const float4*>(Ssm + i * ld);
+            float4 v = row[0];
+            float acc = f_add(f_add(f_add(v.x, v.y), v.z), v.w);
+#pragma unroll 4
+            for (int c = 1; c < G; ++c) {
+                v = row[c];
+                acc = f_add(f_add(f_add(f_add(acc, v.x), v.y), v.z), v.w);
+            }
             lsum[i] = acc;
         }
     }
     __syncthreads();
 
-    // ---- pass 1: estimates; every thread keeps the largest of its own.  The K-th largest of those <= 384 thread
-    //      maxima (distinct elements) is a lower bound of the K-th largest estimate overall, and with ~25 elements per
-    //      thread it sits at the ~1.5 % quantile: ~150 of the 9,600 estimates lie above it.  Only the thread maxima go
-    //      through the histogram (<= 384 shared-memory atomics per job instead of one per positive element). ----
+    // ---- pass 1: fp32 estimates (written over the copy of S; the raw value is re-read from HBM for the few
+    //      candidates).  Every thread keeps the largest of its ~28 estimates: the K-th largest of those <= 384 thread
+    //      maxima (distinct elements) is a lower bound of the K-th largest estimate overall and sits at the ~1.5 %
+    //      quantile, so only the thread maxima go through the histogram.  Small matrices (fewer than two rows per
+    //      thread: too few thread maxima for a sharp bound) put every positive estimate into the histogram instead. ----
     const int M = nL * nR;
     const int K = M < kTopCorrMinu ? M : kTopCorrMinu;
-    {
+    const bool full_hist = nL < 2 * RP;
+    auto bin_of = [](float a) -> uint32_t {
+        const uint32_t hb = __float_as_uint(a) >> 17;
+        return hb > kSelBinBase ? min(hb - kSelBinBase, (uint32_t)(kSelBins - 1)) : 0u;
+    };
+    if (active) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rsum + 4 * g);
+        const float2 rp0 = make_float2(r4.x + 0.000001f, r4.y + 0.000001f);
+        const float2 rp1 = make_float2(r4.z + 0.000001f, r4.w + 0.000001f);
+        const float2 m1 = make_float2(-1.0f, -1.0f);
         float mymax = 0.0f;
-        int mypos = 0;
-        for (int i = warp; i < nL; i += NW) {
+        for (int i = r0; i < nL; i += RP) {
             const float l = lsum[i];
-            for (int j = lane; j < nR; j += 32) {
-                const float s = Ssm[i * ld + j];
-                if (s > 0.0f) {
-                    const float a = approx_key(s, l, rsum[j]);
-                    Ssm[i * ld + j] = a;  // the raw value is re-read from HBM for the few candidates
-                    mymax = fmaxf(mymax, a);
-                    ++mypos;
-                }
+            float4* sp = reinterpret_cast<float4*>(Ssm + i * ld) + g;
+            const float4 s = *sp;
+            // den = (l + (r + 1e-6)) - s: within 3 ulp of the reference's denominator (s <= l, r: no cancellation)
+            const float2 d0 = __ffma2_rn(make_float2(s.x, s.y), m1, __fadd2_rn(make_float2(l, l), rp0));
+            const float2 d1 = __ffma2_rn(make_float2(s.z, s.w), m1, __fadd2_rn(make_float2(l, l), rp1));
+            float4 a;
+            a.x = s.x * rcp_approx(d0.x);
+            a.y = s.y * rcp_approx(d0.y);
+            a.z = s.z * rcp_approx(d1.x);
+            a.w = s.w * rcp_approx(d1.y);
+            *sp = a;
+            if (full_hist) {
+                if (a.x > 0.0f) atomicAdd(&hist[bin_of(a.x)], 1);
+                if (a.y > 0.0f) atomicAdd(&hist[bin_of(a.y)], 1);
+                if (a.z > 0.0f) atomicAdd(&hist[bin_of(a.z)], 1);
+                if (a.w > 0.0f) atomicAdd(&hist[bin_of(a.w)], 1);
+            } else {
+                mymax = fmaxf(fmaxf(mymax, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
             }
         }
-        if (mymax > 0.0f) {
-            const uint32_t hb = __float_as_uint(mymax) >> 17;
-            atomicAdd(&hist[hb > kSelBinBase ? min(hb - kSelBinBase, (uint32_t)(kSelBins - 1)) : 0u], 1);
-        }
-        mypos = __reduce_add_sync(0xffffffffu, mypos);
-        if (lane == 0 && mypos) atomicAdd(&s_npos, mypos);
+        if (mymax > 0.0f) atomicAdd(&hist[bin_of(mymax)], 1);
     }
     __syncthreads();
-    if (s_npos < K) {  // the 120th value is a zero: ties among zeros decide the order
-        if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
-        return;
-    }
-    if (warp == 0) {  // bin of the K-th largest thread maximum, scanning 32-bin chunks from the top
-        int above = 0, bin = 0;  // fewer than K positive thread maxima: bin 0, every positive estimate is a candidate
+    if (warp == 0) {  // bin of the K-th largest histogram entry, scanning 32-bin chunks from the top
+        int above = 0, bin = 0;  // fewer than K entries: bin 0, every positive estimate is a candidate
         for (int c = kSelBins / 32 - 1; c >= 0; --c) {
             const int h = hist[c * 32 + lane];
             const int tot = __reduce_add_sync(0xffffffffu, h);
@@ -544,69 +548,83 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
             }
             above += tot;
         }
-        if (lane == 0) {
-            s_bin = bin;
-            // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side): at least K
-            // estimates (thread maxima) lie at or above the edge, so the exact K-th largest value does too
-            // (bin 0 collects everything below 2^-16: its lower edge is 0)
-            s_thr = bin > 0 ? __uint_as_float(((uint32_t)bin + kSelBinBase) << 17) * (1.0f - 4e-6f) : 0.0f;
-        }
+        // lower edge of the bin, lowered by 4e-6 relative (estimate error < 1e-6 on either side): at least K
+        // estimates lie at or above the edge, so the exact K-th largest value does too.  Bin 0 collects everything
+        // below 2^-16: every positive estimate is a candidate then (the smallest denormal as the threshold).
+        if (lane == 0) s_thr = bin > 0 ? __uint_as_float(((uint32_t)bin + kSelBinBase) << 17) * (1.0f - 4e-6f) : __uint_as_float(1u);
     }
     __syncthreads();
 
-    // ---- pass 2: candidates ----
-    {
+    // ---- pass 2: candidates (the histogram's storage becomes the candidate list) ----
+    if (active) {
         const float thr = s_thr;
-        for (int i = warp; i < nL; i += NW) {
-            for (int j = lane; j < nR; j += 32) {
-                const float a = Ssm[i * ld + j];  // 0 where S was not positive
-                if (a > 0.0f && a >= thr) {
-                    const int pos = atomicAdd(&s_ncand, 1);
-                    if (pos < kSelMaxCand) cand_e[pos] = i * nR + j;
-                }
+        for (int i = r0; i < nL; i += RP) {
+            const float4 a = *(reinterpret_cast<const float4*>(Ssm + i * ld) + g);
+            if (fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)) >= thr) {
+                const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (av[c] >= thr) {
+                        const int pos = atomicAdd(&s_ncand, 1);
+                        if (pos < kSelMaxCand) cand_ij[pos] = ((uint32_t)i << 16) | (uint32_t)(4 * g + c);
+                    }
             }
         }
     }
     __syncthreads();
     const int nc = s_ncand;
-    if (nc > kSelMaxCand) {  // pathological value distribution: let the slow kernel sort everything
+    if (nc > kSelMaxCand || nc < K) {
+        // pathological value distribution, or the K-th value is not positive (ties among zeros decide the order):
+        // the slow kernel sorts everything
         if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
         return;
     }
-    // ---- the reference's double-precision value (:467) of every candidate, then a bitonic sort of
-    //      (value desc, index asc) keys ----
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(hist);  // 512 keys = the histogram's 4 KB
-    int np2 = 128;
-    while (np2 < nc) np2 <<= 1;
-    __syncthreads();  // histogram no longer needed
-    for (int c = tid; c < np2; c += kSelThreads) {
-        unsigned long long k = 0ull;
+    // ---- the reference's double-precision value (:467) of every candidate ----
+    uint32_t my_ij[2], my_key[2];
+    float my_s[2];
+    const int nc4 = (nc + 3) & ~3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = tid + r * kSelThreads;
+        my_key[r] = 0u;
         if (c < nc) {
-            const int e = cand_e[c];
-            const int i = e / nR, j = e - i * nR;
-            const uint32_t key = exact_key(__ldg(Sg + (size_t)i * np + j), lsum[i], rsum[j]);
-            k = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)e);
+            my_ij[r] = cand_ij[c];
+            const int i = (int)(my_ij[r] >> 16), j = (int)(my_ij[r] & 0xffffu);
+            my_s[r] = __ldg(Sg + (size_t)i * np + j);
+            my_key[r] = exact_key(my_s[r], lsum[i], rsum[j]);
         }
-        skey[c] = k;
+        if (c < nc4) cand_key[c] = my_key[r];  // zero padding to a multiple of four keys
     }
     __syncthreads();
-    block_bitonic_desc<kSelThreads, (kSelMaxCand + kSelThreads - 1) / kSelThreads>(skey, np2);
-    // equal values among the first K (or straddling position K) make the order introsort-specific
-    if (tid < K && tid + 1 < nc && (skey[tid] >> 32) == (skey[tid + 1] >> 32)) s_flag = 1;
-    __syncthreads();
-    if (s_flag) {
-        if (tid == 0) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
-        return;
+    // ---- rank = number of candidates with a larger value.  The candidates contain every element that can be among
+    //      the K largest, so ranks below K are global ranks.  Equal values share a rank and leave the next one empty:
+    //      an empty rank among 0..K means that a tie reaches into the first K positions (or straddles position K), where
+    //      the permutation is introsort-specific (slow kernel). ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = tid + r * kSelThreads;
+        if (c >= nc) break;
+        const uint32_t mine = my_key[r];
+        int gt = 0;
+        const uint4* k4 = reinterpret_cast<const uint4*>(cand_key);
+#pragma unroll 4
+        for (int e = 0; e < nc4 / 4; ++e) {
+            const uint4 k = k4[e];
+            gt += (k.x > mine) + (k.y > mine) + (k.z > mine) + (k.w > mine);
+        }
+        if (gt <= K) s_slot[gt] = 1;
+        if (gt < K) {
+            P.corr_v[job * kTopCorrMinu + gt] = my_s[r];  // the RAW similarity (:486)
+            P.corr_ij[job * kTopCorrMinu + gt] = my_ij[r];
+        }
     }
-    if (tid < K) s_order[tid] = (int)(0xffffffffu - (uint32_t)(skey[tid] & 0xffffffffull));
     __syncthreads();
-    if (tid < K) {
-        const int e = s_order[tid];
-        const int i = e / nR, j = e - i * nR;
-        P.corr_v[job * kTopCorrMinu + tid] = __ldg(Sg + (size_t)i * np + j);
-        P.corr_ij[job * kTopCorrMinu + tid] = ((uint32_t)i << 16) | (uint32_t)j;
+    if (tid < K + (nc > K ? 1 : 0) && s_slot[tid] == 0) s_bad = 1;
+    __syncthreads();
+    if (tid == 0) {
+        if (s_bad) P.slow_jobs[atomicAdd(P.slow_count, 1)] = (int)job;
+        else P.corr_n[job] = K;
     }
-    if (tid == 0) P.corr_n[job] = K;
 }
 
 // Jobs whose order depends on how libstdc++'s introsort permutes equal keys.
