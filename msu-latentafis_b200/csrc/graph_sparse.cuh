@@ -55,16 +55,18 @@ struct SparseWork {
     unsigned char cols[G::CAP];
     unsigned short up_pos[P2];     // first CSR slot right of the diagonal of every row
     unsigned short up_start[P2];   // prefix sums of the rows' counts of pairs a < b
-    union {                        // the bit matrix is dead once the CSR is built: its storage becomes the iteration vectors
+    union alignas(16) {            // the bit matrix is dead once the CSR is built: its storage becomes the iteration vectors
         uint32_t M[G::MAXP][G::NCH];       // bit matrix of possibly connected pairs
         struct {
             float b[G::MAXP], c[G::MAXP];
             unsigned short y[G::MAXP];     // candidates in std::sort order
             unsigned short sel[G::MAXP];   // accepted candidates, acceptance order
-            unsigned long long skeys[P2];  // (b, index) keys of the candidate ranking
+            uint2 buck[P2];                // candidate ranking (block_rank_desc): keys grouped by bucket
+            int start[P2 + 1];             //   and the buckets' first ranks
         } it;
     } u;
-    int wsum[G::NT / 32];
+    unsigned char mark[P2];        // greedy pass: mark[k] == n2 when H[s][k] >= 1e-5 for the candidate s accepted as number n2
+    int wsum[2 * (G::NT / 32)];
     float f;
     int overflow, tie, nsel, npairs;
     // orientation stage (<= 32 survivors), only touched when the introsort replay is needed
@@ -303,10 +305,22 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             w.u.it.c[tid] = acc;
         }
         __syncthreads();
-        if (tid == 0) {
-            float sum = w.u.it.c[0];
-#pragma unroll 8
-            for (int i = 1; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
+        if (tid == 0) {  // c.sum() in index order
+            const float4* c4 = reinterpret_cast<const float4*>(w.u.it.c);
+            float4 v = c4[0];
+            float sum = v.x;
+            if (num >= 4) {
+                sum = f_add(f_add(f_add(sum, v.y), v.z), v.w);
+                int i = 4;
+#pragma unroll 4
+                for (; i + 4 <= num; i += 4) {
+                    v = c4[i >> 2];
+                    sum = f_add(f_add(f_add(f_add(sum, v.x), v.y), v.z), v.w);
+                }
+                for (; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
+            } else {
+                for (int i = 1; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
+            }
             w.f = (float)(1.0 / ((double)sum + 0.00001));
         }
         __syncthreads();
@@ -314,25 +328,21 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
         __syncthreads();
     }
 
-    // ---- order by b descending with std::sort's permutation: (value desc, index asc) keys through the block's
-    //      bitonic sort; equal values that the greedy pass can reach need the introsort replay ----
+    // ---- order by b descending with std::sort's permutation: rank in the order (value desc, index asc) by one bucket
+    //      pass; equal values that the greedy pass can reach need the introsort replay ----
     {
         static_assert(P2 <= NT && G::MAXN <= P2, "one key per thread");
-        unsigned long long k = 0ull;  // padding keys sort last
+        uint32_t key[1] = {0u};
         if (tid < num) {
-            uint32_t u = __float_as_uint(w.u.it.b[tid]);  // b >= 0: the bit pattern orders like the value
-            if (u == 0x80000000u) u = 0u;
-            k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffu - (unsigned)tid);
+            key[0] = __float_as_uint(w.u.it.b[tid]);  // b >= 0: the bit pattern orders like the value
+            if (key[0] == 0x80000000u) key[0] = 0u;
         }
-        if (tid < P2) w.u.it.skeys[tid] = k;
-        __syncthreads();
-        block_bitonic_desc<NT, 1>(w.u.it.skeys, P2);
+        int rank[1], first[1];
+        bool tied[1];
+        block_rank_desc<NT, 1, P2>(key, num, w.u.it.start, w.u.it.buck, reinterpret_cast<uint32_t*>(w.wsum), rank, first, tied);
         if (tid < num) {
-            const unsigned long long me = w.u.it.skeys[tid];
-            w.u.it.y[tid] = (unsigned short)(0xffffu - (unsigned)(me & 0xffffu));
-            if (tid + 1 < num && num > 16 && (me >> 32) == (w.u.it.skeys[tid + 1] >> 32) &&
-                !((double)__uint_as_float((uint32_t)(me >> 32)) < 0.0001))
-                w.tie = 1;
+            w.u.it.y[rank[0]] = (unsigned short)tid;
+            if (tied[0] && num > 16 && !((double)__uint_as_float(key[0]) < 0.0001)) w.tie = 1;
         }
     }
     __syncthreads();
@@ -353,6 +363,8 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             ind[c] = (p < num) ? w.u.it.y[p] : 0;
             if (p < num && !((double)w.u.it.b[ind[c]] < 0.0001)) open |= 1u << c;
         }
+        for (int c = lane; c < P2; c += 32) w.mark[c] = 0;
+        __syncwarp();
         for (;;) {
             int pos = -1;
 #pragma unroll
@@ -364,23 +376,23 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
             const int s = w.u.it.y[pos];
             if (lane == 0) w.u.it.sel[n2] = (unsigned short)s;
             ++n2;
+            if (n2 > 32) break;  // more survivors than the orientation stage holds: dense kernel
+            // H is symmetric: the candidates k with H[k][s] >= 1e-5 (an absent entry is 0) are the entries of row s
+            {
+                const int rs = w.row_start[s], len = w.row_len[s];
+                for (int e = lane; e < len; e += 32)
+                    if (!((double)w.vals[rs + e] < 0.00001)) w.mark[w.cols[rs + e]] = (unsigned char)n2;
+            }
+            __syncwarp();
             const unsigned short sli = w.li[s], srj = w.rj[s];
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 if (!((open >> c) & 1u)) continue;
                 const int p = lane + 32 * c;
-                bool keep = false;
-                if (p != pos && w.li[ind[c]] != sli && w.rj[ind[c]] != srj) {
-                    // H[ind][s] >= 1e-5 ?  (an absent entry is 0)
-                    const int rs = w.row_start[ind[c]], len = w.row_len[ind[c]];
-                    for (int e = 0; e < len; ++e)
-                        if (w.cols[rs + e] == s) {
-                            keep = !((double)w.vals[rs + e] < 0.00001);
-                            break;
-                        }
-                }
+                const bool keep = p != pos && w.li[ind[c]] != sli && w.rj[ind[c]] != srj && w.mark[ind[c]] == (unsigned char)n2;
                 if (!keep) open &= ~(1u << c);
             }
+            __syncwarp();
         }
     }
     __syncwarp();
@@ -547,28 +559,48 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
     const size_t rbase = pair * (size_t)P.lt_stride;
     int num;
     if (nLt > kTopCorrTex) {
-        // ---- K3b: the 200 best rows in std::sort order (matcher.cpp:736-749): bitonic sort of
-        //      (value desc, row asc) keys in the (still unused) CSR value area ----
-        unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.vals);  // <= 1024 keys = 8 KB
-        float* rv = reinterpret_cast<float*>(keys + 1024);                         // [1024]
-        unsigned short* ry = reinterpret_cast<unsigned short*>(rv + 1024);         // [1024]
-        int np2 = 256;
-        while (np2 < nLt) np2 <<= 1;
-        for (int i = tid; i < np2; i += NT) {
-            unsigned long long k = 0ull;
+        // ---- K3b: the 200 best rows in std::sort order (matcher.cpp:736-749): rank of every row maximum in the order
+        //      (value desc, row asc) by one bucket pass, in the (still unused) CSR value area ----
+        constexpr int NB = 512, KPT = 1024 / NT;
+        int* start = reinterpret_cast<int*>(w.vals);                        // [NB + 1] (+ padding to 16 bytes)
+        uint2* buck = reinterpret_cast<uint2*>(start + NB + 4);             // [1024]
+        float* rv = reinterpret_cast<float*>(buck + 1024);                  // [1024]
+        unsigned short* ry = reinterpret_cast<unsigned short*>(start);      // [1024], replay only: the buckets are dead then
+        static_assert(sizeof(int) * (NB + 4) + sizeof(uint2) * 1024 + sizeof(float) * 1024 <= sizeof(w.vals), "K3b scratch");
+        uint32_t key[KPT];
+        float val[KPT];
+#pragma unroll
+        for (int e = 0; e < KPT; ++e) {
+            const int i = tid + e * NT;
+            key[e] = 0u;
+            val[e] = 0.0f;
             if (i < nLt) {
-                const float val = P.rowmax_val[rbase + i];
-                rv[i] = val;
-                k = row_key(val, i, P.rowmax_j[rbase + i]);
+                float x = P.rowmax_val[rbase + i];
+                val[e] = x;
+                rv[i] = x;
+                if (x == 0.0f) x = 0.0f;  // -0 and +0 compare equal in the reference's comparator
+                const uint32_t u = __float_as_uint(x);
+                key[e] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
             }
-            keys[i] = k;
+        }
+        int rank[KPT], first[KPT];
+        bool tied[KPT];
+        block_rank_desc<NT, KPT, NB>(key, nLt, start, buck, reinterpret_cast<uint32_t*>(w.wsum), rank, first, tied);
+        num = kTopCorrTex;
+#pragma unroll
+        for (int e = 0; e < KPT; ++e) {
+            const int i = tid + e * NT;
+            if (i < nLt) {
+                if (rank[e] < kTopCorrTex) {
+                    w.v[rank[e]] = val[e];
+                    w.li[rank[e]] = (unsigned short)i;
+                    w.rj[rank[e]] = P.rowmax_j[rbase + i];
+                }
+                // a tie that reaches into the first 200 positions makes the permutation introsort-specific
+                if (tied[e] && first[e] < kTopCorrTex) w.tie = 1;
+            }
         }
         __syncthreads();
-        block_bitonic_desc<NT, 1024 / NT>(keys, np2);
-        // a tie that reaches into the first 200 positions makes the permutation introsort-specific
-        if (tid < kTopCorrTex && (keys[tid] >> 32) == (keys[tid + 1] >> 32)) w.tie = 1;
-        __syncthreads();
-        num = kTopCorrTex;
         const bool replay = w.tie != 0;
         __syncthreads();
         if (replay) {
@@ -584,12 +616,6 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
                 w.li[tid] = (unsigned short)i;
                 w.rj[tid] = P.rowmax_j[rbase + i];
             }
-        } else if (tid < num) {
-            const unsigned long long k = keys[tid];
-            const int i = 0xffff - (int)((k >> 16) & 0xffffu);
-            w.v[tid] = rv[i];
-            w.li[tid] = (unsigned short)i;
-            w.rj[tid] = (unsigned short)(k & 0xffffu);
         }
     } else {
         num = nLt;
