@@ -72,6 +72,7 @@ struct SparseWork {
     // orientation stage (<= 32 survivors), only touched when the introsort replay is needed
     float s2[32];
     unsigned short y2[32];
+    uint32_t omask[32];            // orientation graph: row masks of the <= 32 survivors
 };
 
 // Cheap, conservative test of "H[a][b] may be non-zero" for all pairs a < b; the exact entry is computed only for the
@@ -328,8 +329,9 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
         __syncthreads();
     }
 
-    // ---- order by b descending with std::sort's permutation: rank in the order (value desc, index asc) by one bucket
-    //      pass; equal values that the greedy pass can reach need the introsort replay ----
+    // ---- order by b descending: rank in the order (value desc, index asc) by one bucket pass.  std::sort's own
+    //      permutation differs from it only inside groups of equal values; the greedy pass below asks for it when -
+    //      and only when - such a group can change its outcome ----
     {
         static_assert(P2 <= NT && G::MAXN <= P2, "one key per thread");
         uint32_t key[1] = {0u};
@@ -340,59 +342,79 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
         int rank[1], first[1];
         bool tied[1];
         block_rank_desc<NT, 1, P2>(key, num, w.u.it.start, w.u.it.buck, reinterpret_cast<uint32_t*>(w.wsum), rank, first, tied);
-        if (tid < num) {
-            w.u.it.y[rank[0]] = (unsigned short)tid;
-            if (tied[0] && num > 16 && !((double)__uint_as_float(key[0]) < 0.0001)) w.tie = 1;
-        }
+        if (tid < num) w.u.it.y[rank[0]] = (unsigned short)tid;
     }
     __syncthreads();
-    if (w.tie) {
-        if (tid == 0) std_sort_desc_emulate<float, unsigned short>(w.u.it.b, w.u.it.y, num);
-        __syncthreads();
-    }
     if (warp != 0) return true;  // the rest runs in warp 0 only; thread 0 carries the result
 
-    // ---- greedy selection (matcher.cpp:1305-1345): lanes own sorted positions p = lane + 32 c ----
+    // ---- greedy selection (matcher.cpp:1305-1345): lanes own sorted positions p = lane + 32 c.  A candidate is
+    //      accepted when it is the first one in sorted order that is still compatible with everything accepted so far
+    //      ("open").  With the open set given, that is the open candidate of largest value whatever the order inside
+    //      groups of equal values - unless another open candidate has the same value.  Only then does std::sort's
+    //      permutation matter (which of the two is accepted first, and in which order they enter the next stage): lane 0
+    //      replays the introsort and the pass starts over on the exact order.  Up to 16 elements std::sort is a stable
+    //      insertion sort and the total order is exact. ----
     int n2 = 0;
     {
         unsigned short ind[CH];
-        unsigned open = 0;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int p = lane + 32 * c;
-            ind[c] = (p < num) ? w.u.it.y[p] : 0;
-            if (p < num && !((double)w.u.it.b[ind[c]] < 0.0001)) open |= 1u << c;
-        }
-        for (int c = lane; c < P2; c += 32) w.mark[c] = 0;
-        __syncwarp();
+        float bv[CH];
+        bool exact = num <= 16;
         for (;;) {
-            int pos = -1;
+            unsigned open = 0;
+            n2 = 0;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const unsigned m = __ballot_sync(0xffffffffu, (open >> c) & 1u);
-                if (m && pos < 0) pos = 32 * c + __ffs(m) - 1;
-            }
-            if (pos < 0) break;
-            const int s = w.u.it.y[pos];
-            if (lane == 0) w.u.it.sel[n2] = (unsigned short)s;
-            ++n2;
-            if (n2 > 32) break;  // more survivors than the orientation stage holds: dense kernel
-            // H is symmetric: the candidates k with H[k][s] >= 1e-5 (an absent entry is 0) are the entries of row s
-            {
-                const int rs = w.row_start[s], len = w.row_len[s];
-                for (int e = lane; e < len; e += 32)
-                    if (!((double)w.vals[rs + e] < 0.00001)) w.mark[w.cols[rs + e]] = (unsigned char)n2;
-            }
-            __syncwarp();
-            const unsigned short sli = w.li[s], srj = w.rj[s];
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                if (!((open >> c) & 1u)) continue;
                 const int p = lane + 32 * c;
-                const bool keep = p != pos && w.li[ind[c]] != sli && w.rj[ind[c]] != srj && w.mark[ind[c]] == (unsigned char)n2;
-                if (!keep) open &= ~(1u << c);
+                ind[c] = (p < num) ? w.u.it.y[p] : 0;
+                bv[c] = (p < num) ? w.u.it.b[ind[c]] : 0.0f;
+                if (p < num && !((double)bv[c] < 0.0001)) open |= 1u << c;
             }
+            for (int c = lane; c < P2; c += 32) w.mark[c] = 0;
             __syncwarp();
+            bool tie_hit = false;
+            for (;;) {
+                int pos = -1;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const unsigned m = __ballot_sync(0xffffffffu, (open >> c) & 1u);
+                    if (m && pos < 0) pos = 32 * c + __ffs(m) - 1;
+                }
+                if (pos < 0) break;
+                const int s = w.u.it.y[pos];
+                if (!exact) {
+                    const float vs = w.u.it.b[s];
+                    bool t = false;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) t |= ((open >> c) & 1u) && lane + 32 * c != pos && bv[c] == vs;
+                    if (__any_sync(0xffffffffu, t)) {
+                        tie_hit = true;
+                        break;
+                    }
+                }
+                if (lane == 0) w.u.it.sel[n2] = (unsigned short)s;
+                ++n2;
+                if (n2 > 32) break;  // more survivors than the orientation stage holds: dense kernel
+                // H is symmetric: the candidates k with H[k][s] >= 1e-5 (an absent entry is 0) are the entries of row s
+                {
+                    const int rs = w.row_start[s], len = w.row_len[s];
+                    for (int e = lane; e < len; e += 32)
+                        if (!((double)w.vals[rs + e] < 0.00001)) w.mark[w.cols[rs + e]] = (unsigned char)n2;
+                }
+                __syncwarp();
+                const unsigned short sli = w.li[s], srj = w.rj[s];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (!((open >> c) & 1u)) continue;
+                    const int p = lane + 32 * c;
+                    const bool keep = p != pos && w.li[ind[c]] != sli && w.rj[ind[c]] != srj && w.mark[ind[c]] == (unsigned char)n2;
+                    if (!keep) open &= ~(1u << c);
+                }
+                __syncwarp();
+            }
+            if (!tie_hit) break;
+            if (lane == 0) std_sort_desc_emulate<float, unsigned short>(w.u.it.b, w.u.it.y, num);
+            __syncwarp();
+            exact = true;
         }
     }
     __syncwarp();
@@ -404,21 +426,31 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
 
     // ---- orientation-consistency graph on the n2 survivors, lane = survivor (acceptance order) ----
     const int me = (lane < n2) ? w.u.it.sel[lane] : w.u.it.sel[0];
-    const float4 mcf = w.cf[me];
-    const float mlo = w.lo[me], mro = w.ro[me], mv = w.v[me];
+    const float mv = w.v[me];
     const unsigned short mli = w.li[me], mrj = w.rj[me];
-    unsigned mask = 0;
-    for (int j = 1; j < n2; ++j) {
-        const float4 ocf = make_float4(__shfl_sync(0xffffffffu, mcf.x, j), __shfl_sync(0xffffffffu, mcf.y, j),
-                                       __shfl_sync(0xffffffffu, mcf.z, j), __shfl_sync(0xffffffffu, mcf.w, j));
-        const float olo = __shfl_sync(0xffffffffu, mlo, j), oro = __shfl_sync(0xffffffffu, mro, j);
-        if (lane < j && angle_compatible(mcf, ocf, mlo, olo, mro, oro)) mask |= 1u << j;
+    // the n2 (n2 - 1) / 2 pairs i < j are spread over the lanes (a pair costs two fdlibm atan2f and six angle
+    // reductions: one round of 32 pairs instead of one round per survivor)
+    w.omask[lane] = 0u;
+    __syncwarp();
+    {
+        const int npair = n2 * (n2 - 1) / 2;
+        for (int e0 = 0; e0 < npair; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < npair) {
+                int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);  // pairs (., j) start at e = j (j - 1) / 2
+                while (j * (j - 1) / 2 > e) --j;
+                while ((j + 1) * j / 2 <= e) ++j;
+                const int i = e - j * (j - 1) / 2;
+                const int ci = w.u.it.sel[i], cj = w.u.it.sel[j];
+                if (angle_compatible(w.cf[ci], w.cf[cj], w.lo[ci], w.lo[cj], w.ro[ci], w.ro[cj])) {
+                    atomicOr(&w.omask[i], 1u << j);
+                    atomicOr(&w.omask[j], 1u << i);
+                }
+            }
+        }
     }
-    for (int j = 0; j < n2; ++j) {  // symmetric half
-        const unsigned mj = __shfl_sync(0xffffffffu, mask, j);
-        if (j < lane && ((mj >> lane) & 1u)) mask |= 1u << j;
-    }
-    if (lane >= n2) mask = 0;
+    __syncwarp();
+    const unsigned mask = (lane < n2) ? w.omask[lane] : 0u;
     float S = (float)(1.0 / (double)n2);  // matcher.cpp:1558
     for (int it = 0; it < 5; ++it) {      // matcher.cpp:1563-1581
         float acc = 0.0f;
@@ -456,9 +488,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
     float score = 0.0f;
     for (;;) {
         // first open sorted position
-        int best = open ? rank : 0x7fffffff;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        const int best = (int)__reduce_min_sync(0xffffffffu, open ? (unsigned)rank : 0x7fffffffu);
         if (best == 0x7fffffff) break;
         const unsigned who = __ballot_sync(0xffffffffu, open && rank == best);
         const int sl = __ffs(who) - 1;  // lane of the accepted survivor
@@ -604,10 +634,12 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
         const bool replay = w.tie != 0;
         __syncthreads();
         if (replay) {
-            if (tid == 0) {
-                std_sort_desc_prefix(DenseKey<float>{rv}, ry, nLt, kTopCorrTex);
-                atomicAdd(P.slow_path_count, 1ull);
-                w.tie = 0;
+            if (tid < 32) {  // warp-cooperative replay of the introsort (stdsort_emul.h)
+                warp_std_sort_desc_prefix(DenseKey<float>{rv}, ry, nLt, kTopCorrTex);
+                if (tid == 0) {
+                    atomicAdd(P.slow_path_count, 1ull);
+                    w.tie = 0;
+                }
             }
             __syncthreads();
             if (tid < num) {
