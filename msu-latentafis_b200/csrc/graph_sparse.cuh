@@ -49,7 +49,6 @@ struct SparseWork {
     float vals[G::CAP];            // CSR values; before the graph is built the texture kernel sorts row maxima here
     float4 cf[G::MAXP];            // candidate coordinates as floats (exact): latent x, rolled x, latent y, rolled y
     float v[G::MAXP];
-    float lo[G::MAXP], ro[G::MAXP];
     unsigned short li[G::MAXP], rj[G::MAXP];
     unsigned short row_start[P2], row_len[G::MAXP];
     unsigned char cols[G::CAP];
@@ -155,7 +154,8 @@ __device__ __forceinline__ bool angle_compatible(float4 c1, float4 c2, float lo1
 // The cascade on the candidate list held in w (v, li, rj, coordinates, orientations).  Returns true
 // when the score (thread 0) is valid, false when the job must go to the dense kernel.
 template <bool LOOKUP>
-__device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __restrict__ table, float* score_out) {
+__device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __restrict__ table, const float* __restrict__ lat_ori,
+                               const float* __restrict__ gal_ori, float* score_out) {
     using G = SparseGeom<LOOKUP>;
     constexpr int NT = G::NT, NW = NT / 32, CH = G::MAXP / 32, P2 = SparseWork<LOOKUP>::P2;
     constexpr int ITERS = LOOKUP ? 3 : 5;  // matcher.cpp:1284 / :1406
@@ -442,7 +442,9 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __re
                 while ((j + 1) * j / 2 <= e) ++j;
                 const int i = e - j * (j - 1) / 2;
                 const int ci = w.u.it.sel[i], cj = w.u.it.sel[j];
-                if (angle_compatible(w.cf[ci], w.cf[cj], w.lo[ci], w.lo[cj], w.ro[ci], w.ro[cj])) {
+                // orientations of the two correspondences' minutiae / texture points (lat_ori, gal_ori: this job's templates)
+                if (angle_compatible(w.cf[ci], w.cf[cj], __ldg(lat_ori + w.li[ci]), __ldg(lat_ori + w.li[cj]), __ldg(gal_ori + w.rj[ci]),
+                                     __ldg(gal_ori + w.rj[cj]))) {
                     atomicOr(&w.omask[i], 1u << j);
                     atomicOr(&w.omask[j], 1u << i);
                 }
@@ -534,8 +536,6 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         const uint32_t lo = P.slot_off[q * 3 + slot] + i, go = P.minu_off[P.g0 + tl] + j;
         const short2 lxy = P.lat_xy[lo], rxy = P.gal_xy[go];
         w.cf[tid] = make_float4((float)lxy.x, (float)rxy.x, (float)lxy.y, (float)rxy.y);
-        w.lo[tid] = P.lat_ori[lo];
-        w.ro[tid] = P.gal_ori[go];
         // the pre-test squares coordinate differences in fp32: exact only below 2048 px
         // (coordinates in [0, 2048): differences below 2048, squared distances below 2^23)
         big = ((unsigned)(int)lxy.x | (unsigned)(int)lxy.y | (unsigned)(int)rxy.x | (unsigned)(int)rxy.y) >= 2048u;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         return;
     }
     float score;
-    const bool ok = sparse_cascade<false>(w, num, nullptr, &score);
+    const bool ok = sparse_cascade<false>(w, num, nullptr, P.lat_ori + P.slot_off[q * 3 + slot], P.gal_ori + P.minu_off[P.g0 + tl], &score);
     if (tid == 0) {
         if (ok) P.comp[((size_t)q * P.G + P.g0 + tl) * 4 + slot] = score;
         else ov.jobs[atomicAdd(ov.count, 1)] = (int)oidx;
@@ -662,14 +662,12 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
         const int i = w.li[tid], j = w.rj[tid];
         const short2 lxy = P.lat_xy[(size_t)q * P.lt_stride + i], rxy = P.gal_xy[gbase + j];
         w.cf[tid] = make_float4((float)lxy.x, (float)rxy.x, (float)lxy.y, (float)rxy.y);
-        w.lo[tid] = P.lat_ori[(size_t)q * P.lt_stride + i];
-        w.ro[tid] = P.gal_ori[gbase + j];
     } else if (tid < SparseGeom<true>::MAXP) {
         w.cf[tid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncthreads();
     float score;
-    const bool ok = sparse_cascade<true>(w, num, P.table, &score);
+    const bool ok = sparse_cascade<true>(w, num, P.table, P.lat_ori + (size_t)q * P.lt_stride, P.gal_ori + gbase, &score);
     if (tid == 0) {
         if (ok) P.comp[((size_t)q * P.G + g) * 4 + 3] = score;
         else ov.jobs[atomicAdd(ov.count, 1)] = (int)pair;

@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
         const float2 rp1 = make_float2(r4.z + 0.000001f, r4.w + 0.000001f);
         const float2 m1 = make_float2(-1.0f, -1.0f);
         float mymax = 0.0f;
+#pragma unroll 2
         for (int i = r0; i < nL; i += RP) {
             const float l = lsum[i];
             float4* sp = reinterpret_cast<float4*>(Ssm + i * ld) + g;
@@ -560,13 +561,14 @@ __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectP
         const float thr = s_thr;
         for (int i = r0; i < nL; i += RP) {
             const float4 a = *(reinterpret_cast<const float4*>(Ssm + i * ld) + g);
-            if (fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)) >= thr) {
+            if (fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)) >= thr) {  // one reservation for the thread's (1..4) candidates
                 const float av[4] = {a.x, a.y, a.z, a.w};
+                int pos = atomicAdd(&s_ncand, (int)(a.x >= thr) + (int)(a.y >= thr) + (int)(a.z >= thr) + (int)(a.w >= thr));
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     if (av[c] >= thr) {
-                        const int pos = atomicAdd(&s_ncand, 1);
                         if (pos < kSelMaxCand) cand_ij[pos] = ((uint32_t)i << 16) | (uint32_t)(4 * g + c);
+                        ++pos;
                     }
             }
         }
