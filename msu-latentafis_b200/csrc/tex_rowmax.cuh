@@ -52,8 +52,8 @@ constexpr int kRowmaxRegs = 128;  // the whole register file: at 96 ptxas serial
 constexpr int kLutBytes = 4 * 256 * 128;  // [s][code][b][row] u8
 constexpr int kWindow = 18;               // see the bound above: 16.002 + 0.4, rounded up with slack
 constexpr int kWindowQ = (kWindow + 3) / 4 + 1;  // the same window on distances tracked as Dq >> 2: floor((x + W) / 4) <= floor(x / 4) + ceil(W / 4) + 1
-constexpr int kCandCap = 192;             // exact re-evaluations per warp and gallery template
-constexpr int kAmbCap = 32;               // (lane, row) re-scans per warp and gallery template
+constexpr int kCandCap = 480;             // exact re-evaluations per warp and gallery template (beyond: every row in full, ~100 x the cost)
+constexpr int kAmbCap = 128;              // (lane, row) re-scans per warp and gallery template
 constexpr int kQLevels = 255;
 
 struct TexWarpState {
