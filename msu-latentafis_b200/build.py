@@ -22,6 +22,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "550"]
 
 
+# dev experiments: extra compiler flags (e.g. LAFIS_EXTRA_NVCC="-DLAFIS_TEX_ADD_MODE=1")
+NVCC_FLAGS += os.environ.get("LAFIS_EXTRA_NVCC", "").split()
+
+
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.isfile(c):

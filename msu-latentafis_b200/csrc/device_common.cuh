@@ -56,6 +56,14 @@ struct HitDev {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Per-(latent, template) kernels run on a grid of (jobs per latent, latents): blockIdx.x is the job inside the latent,
+// the latent is blockIdx.y, with blockIdx.z carrying batches beyond the 65,535 rows of a grid.
+constexpr int kGridLatents = 32768;
+inline dim3 job_grid(unsigned jobs_per_latent, int Q) {
+    return dim3(jobs_per_latent, (unsigned)(Q < kGridLatents ? Q : kGridLatents), (unsigned)((Q + kGridLatents - 1) / kGridLatents));
+}
+__device__ __forceinline__ int job_latent() { return (int)(blockIdx.z * (unsigned)kGridLatents + blockIdx.y); }
+
 // Block-wide bitonic sort of np2 (a power of two, >= 32, <= NT * KPT) 64-bit keys in shared memory, descending.
 // Compare-exchange distances below 32 stay inside a warp: each thread keeps its key(s) in registers and
 // exchanges them by shuffle, so only the distances >= 32 go through shared memory and a block barrier

@@ -267,6 +267,7 @@ struct GraphMinuParams {
     const short2* gal_xy;
     const float* gal_ori;
     int g0, n_chunk;
+    int Q;        // latents of the batch
     int G;        // templates resident on this device
     float* comp;  // [Q][G][4] = score[0], score[1], score[2], score[28]
     // optional (dense kernel only): the surviving correspondences of every job, [job][kTopCorrMinu] x
@@ -341,6 +342,7 @@ struct GraphTexParams {
     const float* gal_ori;
     const float* table;        // [2500]
     int g0, n_chunk;
+    int Q;
     int G;
     float* comp;               // [Q][G][4]; slot 3
     unsigned long long* slow_path_count;

@@ -515,10 +515,11 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
     extern __shared__ __align__(128) unsigned char smem[];
     SparseWork<false>& w = *reinterpret_cast<SparseWork<false>*>(smem);
     const int tid = threadIdx.x;
-    const size_t oidx = blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
-    const int slot = (int)(oidx % 3);
-    const size_t pair = oidx / 3;
-    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+    // grid = (3 * n_chunk, latents)
+    const int q = job_latent();
+    if (q >= P.Q) return;
+    const int tl = (int)(blockIdx.x / 3u), slot = (int)(blockIdx.x - 3u * (unsigned)tl);
+    const size_t oidx = (size_t)q * gridDim.x + blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
     const int num = P.corr_n[oidx];
     if (tid == 0) {
         w.overflow = 0;
@@ -570,8 +571,11 @@ __global__ void __launch_bounds__(SparseGeom<true>::NT) graph_tex_sparse_kernel(
     SparseWork<true>& w = *reinterpret_cast<SparseWork<true>*>(smem);
     constexpr int NT = SparseGeom<true>::NT;
     const int tid = threadIdx.x;
-    const size_t pair = blockIdx.x;
-    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+    // grid = (n_chunk, latents)
+    const int q = job_latent();
+    if (q >= P.Q) return;
+    const int tl = (int)blockIdx.x;
+    const size_t pair = (size_t)q * gridDim.x + blockIdx.x;  // q * n_chunk + tl
     const int g = P.g0 + tl;
     const int nLt = (P.lat_status[q] == 0) ? P.lat_nt[q] : 0;
     const uint32_t gbase = P.tex_off[g];

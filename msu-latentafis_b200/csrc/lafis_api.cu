@@ -1159,7 +1159,7 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             R.slow_jobs = c->slow_jobs.p;
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
             const unsigned jobs = (unsigned)((size_t)Q * n_chunk * 3);
-            minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
+            minu_select_kernel<<<job_grid(3u * (unsigned)n_chunk, Q), kSelThreads, sel_smem, st>>>(R);
             end(2, st);
             begin(6, st);
             minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
@@ -1262,11 +1262,12 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.g0 = g0;
             P.n_chunk = n_chunk;
             P.G = G;
+            P.Q = Q;
             P.comp = c->comp.p;
             P.dense_jobs_total = c->d_slow + 2;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, sizeof(int), st));
-            graph_minu_sparse_kernel<<<grid, SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
+            graph_minu_sparse_kernel<<<job_grid(3u * (unsigned)n_chunk, Q), SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
                 P, OverflowList{c->d_ov_count, c->ov_minu.p});
             end(3, st);
             begin(7, st);
@@ -1293,11 +1294,12 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.g0 = g0;
             P.n_chunk = n_chunk;
             P.G = G;
+            P.Q = Q;
             P.comp = c->comp.p;
             P.slow_path_count = c->d_slow + 1;
             P.dense_jobs_total = c->d_slow + 3;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk);
-            graph_tex_sparse_kernel<<<grid, SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
+            graph_tex_sparse_kernel<<<job_grid((unsigned)n_chunk, Q), SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
                 P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
             graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, sb>>>(
                 P, c->d_ov_count + 1, c->ov_tex.p);
@@ -1438,7 +1440,7 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     R.slow_count = c->d_slow_count;
     R.slow_jobs = c->slow_jobs.p;
     LAFIS_CUDA(c, cudaMemsetAsync(c->d_slow_count, 0, sizeof(int), st));
-    minu_select_kernel<<<jobs, kSelThreads, sel_smem, st>>>(R);
+    minu_select_kernel<<<job_grid(3u, Q), kSelThreads, sel_smem, st>>>(R);
     minu_select_slow_kernel<<<std::min<unsigned>(jobs, (unsigned)c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
     if (nR_gi > 0 && L->status[q] == LAFIS_OK && (nR_gi > plan.r_cap || L->max_slot_n > plan.l_cap)) {
         std::vector<int> bj;
@@ -1485,6 +1487,7 @@ static int run_correspondences(lafis_ctx* c, lafis_latents* L, int q, int gi, sh
     Gp.g0 = gi;
     Gp.n_chunk = 1;
     Gp.G = G;
+    Gp.Q = Q;
     Gp.comp = c->comp.p;
     Gp.corr_out = c->corr_xy.p;
     Gp.corr_out_n = c->corr_xy_n.p;

@@ -98,7 +98,7 @@ __device__ __forceinline__ void sim_tile(const float* __restrict__ As, int tile0
     for (int a = 0; a < RT; ++a)
 #pragma unroll
         for (int b = 0; b < NC; ++b) acc[a][b] = 0.0f;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < 96; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(pa8);
         const float4 a1 = *reinterpret_cast<const float4*>(pa8 + 4);
@@ -420,10 +420,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __global__ void __launch_bounds__(kSelThreads, 4) minu_select_kernel(MinuSelectParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t job = blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
-    const int slot = (int)(job % 3);
-    const size_t pair = job / 3;
-    const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+    // grid = (3 * n_chunk, latents): no run-time division in the job decode (job_grid, device_common.cuh)
+    const int q = job_latent();
+    if (q >= P.Q) return;
+    const int tl = (int)(blockIdx.x / 3u), slot = (int)(blockIdx.x - 3u * (unsigned)tl);
+    const size_t job = (size_t)q * gridDim.x + blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
     const int nR = P.minu_n[P.g0 + tl];
     const int nL = (P.lat_status[q] == 0) ? P.slot_n[q * 3 + slot] : 0;
     if (nL <= 0 || nR <= 0 || nL > P.l_cap || nR > P.r_cap) {
