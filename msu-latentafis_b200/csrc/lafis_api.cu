@@ -123,6 +123,13 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     ok = ok && cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    {
+        int lo_pri = 0, hi_pri = 0;  // the few rare-path CTAs should take free SM resources ahead of the main stream's
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        ok = ok && cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, hi_pri) == cudaSuccess;
+        for (cudaEvent_t* ev : {&c->ev_sel, &c->ev_slow, &c->ev_gtex, &c->ev_gtexd})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (const char* e2 = getenv("LAFIS_STREAMS")) c->two_streams = atoi(e2) >= 2;
     ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
@@ -251,6 +258,9 @@ void lafis_destroy(lafis_ctx* c) {
     if (c->stream_b) cudaStreamDestroy(c->stream_b);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream_c) cudaStreamDestroy(c->stream_c);
+    for (cudaEvent_t ev : {c->ev_sel, c->ev_slow, c->ev_gtex, c->ev_gtexd})
+        if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1081,6 +1091,13 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     static const bool force_two = getenv("LAFIS_FORCE_TWO_STREAMS") != nullptr;  // experiment switch
     const bool two = c->two_streams && (n_chunks > 1 || force_two);
     cudaStream_t sb = two ? c->stream_b : st;
+    // Rare-path kernels on their own (high-priority) stream: the selection's introsort replays run next to the texture
+    // graph kernel, the dense texture graphs next to the minutiae graph kernel, instead of a few long jobs holding up the
+    // 300,000-CTA kernel behind them (0.8 ms of 68 per 100,000 pairs).  Not with oversized pairs (their host-built work
+    // lists follow the replay kernel on the main stream) and not in the serialised mode (lafis_set_streams(ctx, 1)).
+    const bool tails = c->two_streams && !has_big;
+    cudaStream_t sc = tails ? c->stream_c : st;
+    bool tail_pending = false;  // an earlier chunk's dense texture graphs may still read the overflow list
     auto begin = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage], s_); };
     auto end = [&](int stage, cudaStream_t s_) { cudaEventRecord(c->stage_ev[16 * chunk_id + 2 * stage + 1], s_); };
     if (two) {  // the texture chain starts once the latent batch is in HBM
@@ -1161,8 +1178,13 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             const unsigned jobs = (unsigned)((size_t)Q * n_chunk * 3);
             minu_select_kernel<<<job_grid(3u * (unsigned)n_chunk, Q), kSelThreads, sel_smem, st>>>(R);
             end(2, st);
-            begin(6, st);
-            minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, st>>>(R, c->d_slow);
+            if (tails) {
+                LAFIS_CUDA(c, cudaEventRecord(c->ev_sel, st));
+                LAFIS_CUDA(c, cudaStreamWaitEvent(sc, c->ev_sel, 0));
+            }
+            begin(6, sc);
+            minu_select_slow_kernel<<<std::min<unsigned>(jobs, 2u * c->sm_count), kSelThreads, slow_smem, sc>>>(R, c->d_slow);
+            if (tails) LAFIS_CUDA(c, cudaEventRecord(c->ev_slow, sc));
             if (has_big) {
                 // work list of this chunk: every (latent, slot) against the oversized templates, and oversized
                 // latent slots against every template
@@ -1208,8 +1230,10 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
                 if (rc_big != LAFIS_OK) return rc_big;
             }
         }
-        end(6, st);
+        end(6, sc);
         // ---- texture chain (stream sb): K2 + K3a, then K3b + K4 + K9 ----
+        if (tail_pending)  // the previous chunk's dense texture graphs read the row maxima and the overflow list
+            LAFIS_CUDA(c, cudaStreamWaitEvent(sb, c->ev_gtexd, 0));
         begin(0, sb);
         {
             TexRowmaxParams P;
@@ -1246,6 +1270,47 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             tex_rowmax_kernel<<<grid, kRowmaxThreads, kRowmaxSmem, sb>>>(P);
         }
         end(0, sb);
+        begin(4, sb);
+        // ---- K3b + K4 + K9 (texture) ----
+        {
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count + 1, 0, sizeof(int), sb));
+            GraphTexParams P;
+            P.rowmax_val = c->rowmax_val.p;
+            P.rowmax_j = c->rowmax_j.p;
+            P.lt_stride = L->lt_stride;
+            P.lat_nt = D.tex_n;
+            P.lat_status = D.status;
+            P.lat_xy = D.tex_xy;
+            P.lat_ori = D.tex_ori;
+            P.tex_off = c->gal.tex_off;
+            P.gal_xy = c->gal.tex_xy;
+            P.gal_ori = c->gal.tex_ori;
+            P.table = c->d_table;
+            P.g0 = g0;
+            P.n_chunk = n_chunk;
+            P.G = G;
+            P.Q = Q;
+            P.comp = c->comp.p;
+            P.slow_path_count = c->d_slow + 1;
+            P.dense_jobs_total = c->d_slow + 3;
+            const unsigned grid = (unsigned)((size_t)Q * n_chunk);
+            graph_tex_sparse_kernel<<<job_grid((unsigned)n_chunk, Q), SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
+                P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
+            cudaStream_t sd = sb;
+            if (tails) {  // the few dense jobs run next to the minutiae graph kernel
+                LAFIS_CUDA(c, cudaEventRecord(c->ev_gtex, sb));
+                LAFIS_CUDA(c, cudaStreamWaitEvent(sc, c->ev_gtex, 0));
+                sd = sc;
+            }
+            graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, sd>>>(
+                P, c->d_ov_count + 1, c->ov_tex.p);
+            end(4, sd);
+            if (tails) {
+                LAFIS_CUDA(c, cudaEventRecord(c->ev_gtexd, sc));
+                tail_pending = true;
+            }
+        }
+        if (tails) LAFIS_CUDA(c, cudaStreamWaitEvent(st, c->ev_slow, 0));  // the replayed jobs' candidate lists
         begin(3, st);
         // ---- K8 + K9 (minutiae) ----
         {
@@ -1275,36 +1340,6 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
                 P, c->d_ov_count, c->ov_minu.p);
         }
         end(7, st);
-        begin(4, sb);
-        // ---- K3b + K4 + K9 (texture) ----
-        {
-            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count + 1, 0, sizeof(int), sb));
-            GraphTexParams P;
-            P.rowmax_val = c->rowmax_val.p;
-            P.rowmax_j = c->rowmax_j.p;
-            P.lt_stride = L->lt_stride;
-            P.lat_nt = D.tex_n;
-            P.lat_status = D.status;
-            P.lat_xy = D.tex_xy;
-            P.lat_ori = D.tex_ori;
-            P.tex_off = c->gal.tex_off;
-            P.gal_xy = c->gal.tex_xy;
-            P.gal_ori = c->gal.tex_ori;
-            P.table = c->d_table;
-            P.g0 = g0;
-            P.n_chunk = n_chunk;
-            P.G = G;
-            P.Q = Q;
-            P.comp = c->comp.p;
-            P.slow_path_count = c->d_slow + 1;
-            P.dense_jobs_total = c->d_slow + 3;
-            const unsigned grid = (unsigned)((size_t)Q * n_chunk);
-            graph_tex_sparse_kernel<<<job_grid((unsigned)n_chunk, Q), SparseGeom<true>::NT, sizeof(SparseWork<true>), sb>>>(
-                P, OverflowList{c->d_ov_count + 1, c->ov_tex.p});
-            graph_tex_dense_kernel<<<std::min<unsigned>(grid, (unsigned)c->sm_count), kGraphTexThreads, kGraphTexSmem, sb>>>(
-                P, c->d_ov_count + 1, c->ov_tex.p);
-        }
-        end(4, sb);
         c->stats.kernel_launches += 8;
         LAFIS_CUDA(c, cudaGetLastError());
         ++chunk_id;
@@ -1314,6 +1349,7 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         LAFIS_CUDA(c, cudaEventRecord(c->ev_join, sb));
         LAFIS_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     }
+    if (tail_pending) LAFIS_CUDA(c, cudaStreamWaitEvent(st, c->ev_gtexd, 0));
     // ---- K10 ----
     cudaEventRecord(c->stage_ev[16 * n_chunks], st);
     {

@@ -96,6 +96,10 @@ struct lafis_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_b = nullptr;  // texture chain runs here, concurrently with the minutiae chain on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // rare-path kernels (introsort replays of the selection, dense texture graphs: a few hundred long jobs on <= 2 CTAs per
+    // SM) run here, next to the following many-CTA kernel of the main stream instead of holding it up
+    cudaStream_t stream_c = nullptr;
+    cudaEvent_t ev_sel = nullptr, ev_slow = nullptr, ev_gtex = nullptr, ev_gtexd = nullptr;
     bool two_streams = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_ev;  // 16 per pipeline chunk + 2 for the tail, grown on demand
