@@ -277,6 +277,7 @@ def cli_legs(T, cb, rolled, latent, n_files: int):
                        "what": "bin/match -ldir: process start, CUDA context, codebook, parallel ingest of the directory "
                                "into HBM, match, score file; wall clock of the whole process",
                        "ingest": ingest[-1] if ingest else None,
+                       "stamps": [l[len("lafis cli: "):] for l in r.stderr.split("\n") if l.startswith("lafis cli: ")],
                        "score_file_identical_to_reference_cli": (outs.get("ref") == outs["b200"]) if "ref" in outs else None}
         return shipped, cli
     finally:

@@ -359,6 +359,7 @@ int one2list(Engine& E, const char* latent_template_file, const char* rolled_dir
     output.close();
     const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
     std::cout << "Total matching duration (ms): " << span.count() << std::endl;
+    if (getenv("LAFIS_INGEST_TIMING")) std::cerr << "lafis cli: matching (gallery resident) took " << span.count() << " ms" << std::endl;
     return LAFIS_OK;
 }
 
@@ -437,6 +438,7 @@ int list2list(Engine& E, const char* latent_dir, const char* rolled_dir, const c
     }
     const std::chrono::duration<double, std::milli> span = std::chrono::high_resolution_clock::now() - t0;
     std::cout << "Total matching duration (ms): " << span.count() << std::endl;
+    if (getenv("LAFIS_INGEST_TIMING")) std::cerr << "lafis cli: matching (gallery resident) took " << span.count() << " ms" << std::endl;
     return LAFIS_OK;
 }
 

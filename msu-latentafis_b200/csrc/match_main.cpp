@@ -5,6 +5,7 @@
 // -gpus N (or LAFIS_GPUS=N) shards the gallery over devices 0..N-1 of this process (contiguous index ranges,
 // one NCCL all-gather per match, score rows gathered to device 0); the files written are the same, byte for byte.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <filesystem>
 #include <fstream>
@@ -53,6 +54,15 @@ std::string config_value(const std::string& text, const std::string& key) {
 }  // namespace
 
 int main(int argc, char** argv) {
+    // LAFIS_INGEST_TIMING: where a cold process spends its time (stderr, next to the ingest line of the library)
+    const bool timing = std::getenv("LAFIS_INGEST_TIMING") != nullptr;
+    const auto t_main = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (timing)
+            std::cerr << "lafis cli: " << what << " at "
+                      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count() << " ms"
+                      << std::endl;
+    };
     std::string config;
     {
         std::ifstream in((fs::current_path().parent_path() / "afis.config").string());
@@ -70,6 +80,7 @@ int main(int argc, char** argv) {
     lafis_ctx* ctx = nullptr;
     lafis_group* group = nullptr;
     int rc = n_gpus > 1 ? lafis_group_create(codebook.c_str(), nullptr, n_gpus, &group) : lafis_create(codebook.c_str(), device, &ctx);
+    stamp("matcher created (CUDA context, module, codebook)");
     if (rc != LAFIS_OK) {
         std::cerr << "match: cannot create matcher (status " << rc << "): " << lafis_last_error(nullptr) << "; codebook '"
                   << codebook << "', CUDA device " << device << ", " << n_gpus << " GPU(s) (sm_100 GPUs are required)"
@@ -104,10 +115,12 @@ int main(int argc, char** argv) {
         rc = group ? lafis_group_list2list_matching(group, ldir.c_str(), gallery_path.c_str(), score_path.c_str())
                    : lafis_list2list_matching(ctx, ldir.c_str(), gallery_path.c_str(), score_path.c_str());
     }
+    stamp("driver returned (ingest, match, files written)");
     if (rc < LAFIS_ERR_NO_TEMPLATES)
         std::cerr << "match: " << (group ? lafis_group_last_error(group) : lafis_last_error(ctx)) << " (status " << rc << ")"
                   << std::endl;
     if (group) lafis_group_destroy(group);
     else lafis_destroy(ctx);
+    stamp("matcher destroyed");
     return 0;  // matching/main.cpp:86 ignores the drivers' return codes
 }

@@ -262,7 +262,7 @@ def test_group_over_all_visible_gpus(pkg, matcher, golden, tmp_path):
     cbp = os.path.join(str(tmp_path), "cb.dat")
     T.write_codebook(cbp, cb)
     n_dev = n_gpus()
-    rolled, latents = _synthetic_set(pkg, cb, n=3 * n_dev + 5, seed=2100)
+    rolled, latents = _synthetic_set(pkg, cb, n=max(3 * n_dev + 5, 23), seed=2100)  # the latents mate with prints 0, 7, 14, 21
     gdir, ldir, gp, lp = _write_files(pkg, rolled, latents[:2], str(tmp_path))
     matcher.load_gallery_files(gp)
     one = matcher.match(matcher.load_latents(lp), topk=10)
