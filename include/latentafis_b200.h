@@ -332,8 +332,10 @@ typedef struct {
     uint64_t minu_big_jobs;   /* (latent, template, minutiae slot) jobs too large for the shared-memory tiles, scored
                                  by the HBM-resident kernels (same results, slower) */
     uint64_t graph_minu_dense_jobs; /* minutiae pruning jobs whose consistency graph did not fit the sparse kernel
-                                       (mated or near-duplicate prints): dense kernel, same result, ~50 us each */
+                                       (mated or near-duplicate prints): dense kernel, same result, ~100 us each */
     uint64_t graph_tex_dense_jobs;  /* the same for the texture component */
+    uint64_t graph_minu_mid_jobs;   /* minutiae pruning jobs beyond the first sparse kernel's 2,560 non-zeros, retried with
+                                       6,656 (clustered minutiae); graph_minu_dense_jobs counts what that left over */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
 /* 2 (default): when a match runs in several pipeline chunks the texture chain runs on a second CUDA stream

@@ -26,14 +26,18 @@
 
 namespace lafis {
 
-template <bool LOOKUP>
+template <bool LOOKUP, int TIER = 0>
 struct SparseGeom;
 template <>
-struct SparseGeom<false> {  // minutiae: <= 120 candidates
+struct SparseGeom<false, 0> {  // minutiae: <= 120 candidates
     static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 2560, NCH = 4;
 };
 template <>
-struct SparseGeom<true> {  // texture: <= 200 candidates
+struct SparseGeom<false, 1> {  // minutiae, second chance for denser graphs (clustered minutiae): 46 % of the full matrix, 5 CTAs per SM
+    static constexpr int MAXN = kTopCorrMinu, MAXP = 128, NT = 128, CAP = 6656, NCH = 4;
+};
+template <>
+struct SparseGeom<true, 0> {  // texture: <= 200 candidates
     static constexpr int MAXN = kTopCorrTex, MAXP = 224, NT = 256, CAP = 4352, NCH = 7;
 };
 
@@ -42,9 +46,9 @@ struct SparseGeom<true> {  // texture: <= 200 candidates
 // accumulator flushed with one shared-memory atomic per row chunk); the exact entries are then computed ONCE per
 // surviving pair, the pairs spread evenly over all threads, and stored at both CSR positions, which follow from
 // popcounts of the two bit rows.
-template <bool LOOKUP>
+template <bool LOOKUP, int TIER = 0>
 struct SparseWork {
-    using G = SparseGeom<LOOKUP>;
+    using G = SparseGeom<LOOKUP, TIER>;
     static constexpr int P2 = G::MAXP <= 128 ? 128 : 256;
     float vals[G::CAP];            // CSR values; before the graph is built the texture kernel sorts row maxima here
     float4 cf[G::MAXP];            // candidate coordinates as floats (exact): latent x, rolled x, latent y, rolled y
@@ -153,11 +157,11 @@ __device__ __forceinline__ bool angle_compatible(float4 c1, float4 c2, float lo1
 
 // The cascade on the candidate list held in w (v, li, rj, coordinates, orientations).  Returns true
 // when the score (thread 0) is valid, false when the job must go to the dense kernel.
-template <bool LOOKUP>
-__device__ bool sparse_cascade(SparseWork<LOOKUP>& w, int num, const float* __restrict__ table, const float* __restrict__ lat_ori,
+template <bool LOOKUP, int TIER>
+__device__ bool sparse_cascade(SparseWork<LOOKUP, TIER>& w, int num, const float* __restrict__ table, const float* __restrict__ lat_ori,
                                const float* __restrict__ gal_ori, float* score_out) {
-    using G = SparseGeom<LOOKUP>;
-    constexpr int NT = G::NT, NW = NT / 32, CH = G::MAXP / 32, P2 = SparseWork<LOOKUP>::P2;
+    using G = SparseGeom<LOOKUP, TIER>;
+    constexpr int NT = G::NT, NW = NT / 32, CH = G::MAXP / 32, P2 = SparseWork<LOOKUP, TIER>::P2;
     constexpr int ITERS = LOOKUP ? 3 : 5;  // matcher.cpp:1284 / :1406
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     *score_out = 0.0f;
@@ -511,22 +515,19 @@ struct OverflowList {
     int* jobs;
 };
 
-__global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kernel(GraphMinuParams P, OverflowList ov) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    SparseWork<false>& w = *reinterpret_cast<SparseWork<false>*>(smem);
+// one (latent, template, slot) job; a job the working set cannot hold is appended to `ov`
+template <int TIER>
+__device__ __forceinline__ void graph_minu_job(SparseWork<false, TIER>& w, const GraphMinuParams& P, size_t oidx, int q, int tl, int slot,
+                                               OverflowList ov) {
+    using G = SparseGeom<false, TIER>;
     const int tid = threadIdx.x;
-    // grid = (3 * n_chunk, latents)
-    const int q = job_latent();
-    if (q >= P.Q) return;
-    const int tl = (int)(blockIdx.x / 3u), slot = (int)(blockIdx.x - 3u * (unsigned)tl);
-    const size_t oidx = (size_t)q * gridDim.x + blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
     const int num = P.corr_n[oidx];
     if (tid == 0) {
         w.overflow = 0;
         w.tie = 0;
         w.npairs = 0;
     }
-    for (int e = tid; e < SparseGeom<false>::MAXP * SparseGeom<false>::NCH; e += SparseGeom<false>::NT) (&w.u.M[0][0])[e] = 0u;
+    for (int e = tid; e < G::MAXP * G::NCH; e += G::NT) (&w.u.M[0][0])[e] = 0u;
     int big = 0;
     if (tid < num) {
         const uint32_t ij = P.corr_ij[oidx * kTopCorrMinu + tid];
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
         // the pre-test squares coordinate differences in fp32: exact only below 2048 px
         // (coordinates in [0, 2048): differences below 2048, squared distances below 2^23)
         big = ((unsigned)(int)lxy.x | (unsigned)(int)lxy.y | (unsigned)(int)rxy.x | (unsigned)(int)rxy.y) >= 2048u;
-    } else if (tid < SparseGeom<false>::MAXP) {
+    } else if (tid < G::MAXP) {
         w.cf[tid] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (__syncthreads_or(big)) {  // larger images: the dense kernel evaluates every entry exactly
@@ -552,6 +553,37 @@ __global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kerne
     if (tid == 0) {
         if (ok) P.comp[((size_t)q * P.G + P.g0 + tl) * 4 + slot] = score;
         else ov.jobs[atomicAdd(ov.count, 1)] = (int)oidx;
+    }
+}
+
+__global__ void __launch_bounds__(SparseGeom<false>::NT) graph_minu_sparse_kernel(GraphMinuParams P, OverflowList ov) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    SparseWork<false>& w = *reinterpret_cast<SparseWork<false>*>(smem);
+    // grid = (3 * n_chunk, latents)
+    const int q = job_latent();
+    if (q >= P.Q) return;
+    const int tl = (int)(blockIdx.x / 3u), slot = (int)(blockIdx.x - 3u * (unsigned)tl);
+    const size_t oidx = (size_t)q * gridDim.x + blockIdx.x;  // (q * n_chunk + tl) * 3 + slot
+    graph_minu_job<0>(w, P, oidx, q, tl, slot, ov);
+}
+
+// Second chance for the jobs whose graph overflowed the 2,560 non-zeros of the kernel above (prints with clustered
+// minutiae: SURVEY 8d's i.i.d. gallery has ~1,300): the same cascade over a CSR of 6,656 non-zeros at 5 CTAs per SM,
+// ~4 x cheaper than the dense kernel, which remains for what is left (mated pairs, large images, > 32 survivors).
+__global__ void __launch_bounds__(SparseGeom<false, 1>::NT) graph_minu_mid_kernel(GraphMinuParams P, const int* in_count,
+                                                                                  const int* in_jobs, OverflowList ov,
+                                                                                  unsigned long long* mid_jobs_total) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    SparseWork<false, 1>& w = *reinterpret_cast<SparseWork<false, 1>*>(smem);
+    const int n_jobs = *in_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && mid_jobs_total) atomicAdd(mid_jobs_total, (unsigned long long)n_jobs);
+    for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        const size_t oidx = (size_t)in_jobs[jb];  // (q * n_chunk + tl) * 3 + slot
+        const int slot = (int)(oidx % 3);
+        const size_t pair = oidx / 3;
+        const int tl = (int)(pair % P.n_chunk), q = (int)(pair / P.n_chunk);
+        __syncthreads();  // the previous job's working set is no longer in use
+        graph_minu_job<1>(w, P, oidx, q, tl, slot, ov);
     }
 }
 

@@ -67,7 +67,7 @@ void size_work_budget(lafis_ctx* c) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
     const size_t held = sizeof(float) * (c->sim.cap + c->rowmax_val.cap + c->corr_v.cap) + 2 * c->rowmax_j.cap +
-                        4 * (c->corr_ij.cap + c->corr_n.cap + c->slow_jobs.cap + c->ov_minu.cap + c->ov_tex.cap);
+                        4 * (c->corr_ij.cap + c->corr_n.cap + c->slow_jobs.cap + c->ov_minu.cap + c->ov_minu2.cap + c->ov_tex.cap);
     c->work_budget = std::min<size_t>(std::max<size_t>((free_b + held) / 2, (size_t)1 << 30), (size_t)64 << 30);
 }
 
@@ -135,9 +135,9 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
     ok = ok && cudaMalloc(&c->d_codebook, sizeof(float) * kSubs * kClusters * kSubDim) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_table, sizeof(float) * kTableN * kTableN) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_job_counter, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_ov_count, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_ov_count, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->d_slow_count, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->d_slow, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_slow, 12 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) {
         // matcher.cpp:49-56: table[i*50+j] = (float)sqrt((16 i)^2 + (16 j)^2), square root in double
         std::vector<float> table(kTableN * kTableN);
@@ -147,7 +147,7 @@ int create_common(const float* codewords, int device, lafis_ctx** out) {
         ok = cudaMemcpy(c->d_table, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemcpy(c->d_codebook, codewords, sizeof(float) * kSubs * kClusters * kSubDim,
                               cudaMemcpyHostToDevice) == cudaSuccess;
-        ok = ok && cudaMemset(c->d_slow, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(c->d_slow, 0, 12 * sizeof(unsigned long long)) == cudaSuccess;
         TRY(cudaFuncSetAttribute(tex_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowmaxSmem));
         TRY(cudaFuncSetAttribute(minu_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         TRY(cudaFuncSetAttribute(minu_sim_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -223,6 +223,7 @@ void lafis_destroy(lafis_ctx* c) {
     c->slow_jobs.release();
     cudaFree(c->d_slow_count);
     c->ov_minu.release();
+    c->ov_minu2.release();
     c->ov_tex.release();
     cudaFree(c->d_ov_count);
     c->comp.release();
@@ -1070,6 +1071,7 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     LAFIS_CUDA(c, c->sim.reserve((size_t)Q * n_chunk_max * 3 * job_stride));
     LAFIS_CUDA(c, c->slow_jobs.reserve((size_t)Q * n_chunk_max * 3));
     LAFIS_CUDA(c, c->ov_minu.reserve((size_t)Q * n_chunk_max * 3));
+    LAFIS_CUDA(c, c->ov_minu2.reserve((size_t)Q * n_chunk_max * 3));
     LAFIS_CUDA(c, c->ov_tex.reserve((size_t)Q * n_chunk_max));
     LAFIS_CUDA(c, c->comp.reserve((size_t)Q * G * 4));
     LAFIS_CUDA(c, c->final_scores.reserve((size_t)Q * G));
@@ -1332,15 +1334,19 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             P.dense_jobs_total = c->d_slow + 2;
             const unsigned grid = (unsigned)((size_t)Q * n_chunk * 3);
             LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count, 0, sizeof(int), st));
+            LAFIS_CUDA(c, cudaMemsetAsync(c->d_ov_count + 2, 0, sizeof(int), st));
             graph_minu_sparse_kernel<<<job_grid(3u * (unsigned)n_chunk, Q), SparseGeom<false>::NT, sizeof(SparseWork<false>), st>>>(
                 P, OverflowList{c->d_ov_count, c->ov_minu.p});
             end(3, st);
             begin(7, st);
+            // overflowed jobs: second chance with a larger CSR, then the dense kernel for what is left
+            graph_minu_mid_kernel<<<std::min<unsigned>(grid, 5u * c->sm_count), SparseGeom<false, 1>::NT, sizeof(SparseWork<false, 1>), st>>>(
+                P, c->d_ov_count, c->ov_minu.p, OverflowList{c->d_ov_count + 2, c->ov_minu2.p}, c->d_slow + 8);
             graph_minu_dense_kernel<<<std::min<unsigned>(grid, 2u * c->sm_count), kGraphMinuThreads, kGraphMinuSmem, st>>>(
-                P, c->d_ov_count, c->ov_minu.p);
+                P, c->d_ov_count + 2, c->ov_minu2.p);
         }
         end(7, st);
-        c->stats.kernel_launches += 8;
+        c->stats.kernel_launches += 9;
         LAFIS_CUDA(c, cudaGetLastError());
         ++chunk_id;
     }
@@ -1554,8 +1560,9 @@ void lafis::collect_times(lafis_ctx* c) {
     cudaEventElapsedTime(&t, c->stage_ev[16 * c->stage_chunks], c->stage_ev[16 * c->stage_chunks + 1]);
     ms[5] = t;
     std::memcpy(c->stats.last_stage_ms, ms, sizeof ms);
-    unsigned long long cnt[8];
+    unsigned long long cnt[12];
     if (cudaMemcpy(cnt, c->d_slow, sizeof cnt, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        c->stats.graph_minu_mid_jobs = cnt[8];
         c->stats.minu_replays = cnt[0];
         c->stats.tex_replays = cnt[1];
         c->stats.graph_minu_dense_jobs = cnt[2];

@@ -139,7 +139,8 @@ struct lafis_ctx {
     lafis::DevBuf<int> slow_jobs;        // selection jobs that need the introsort replay
     int* d_slow_count = nullptr;
     lafis::DevBuf<int> ov_minu, ov_tex;  // overflow job lists of the sparse graph kernels
-    int* d_ov_count = nullptr;           // [2]
+    lafis::DevBuf<int> ov_minu2;         // ... of the second-chance minutiae kernel (graph_minu_mid_kernel): the dense kernel's list
+    int* d_ov_count = nullptr;           // [4]: 0 minutiae, 1 texture, 2 minutiae second chance
     lafis::DevBuf<float> comp;
     lafis::DevBuf<float> final_scores;
     lafis::DevBuf<short4> corr_xy;       // lafis_correspondences: surviving correspondences of the 3 minutiae components
@@ -157,7 +158,7 @@ struct lafis_ctx {
     lafis::DevBuf<float> big_S;
     lafis::DevBuf<uint32_t> big_keys, big_order;
     int* d_job_counter = nullptr;
-    unsigned long long* d_slow = nullptr;  // [8] counters: 0 minutiae introsort replays, 1 texture top-200 replays,
+    unsigned long long* d_slow = nullptr;  // [12] counters (8: jobs of the second-chance minutiae graph kernel): 0 minutiae introsort replays, 1 texture top-200 replays,
                                            //     4..7 texture row-max: queued, exact evaluations, overflowed, templates
 
     // multi-GPU (sharded.cu)

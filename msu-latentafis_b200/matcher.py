@@ -85,7 +85,7 @@ class _Stats(C.Structure):
                 ("last_stage_ms", C.c_float * 8), ("minu_replays", C.c_uint64), ("tex_replays", C.c_uint64),
                 ("tex_queued", C.c_uint64), ("tex_exact", C.c_uint64), ("tex_overflow", C.c_uint64),
                 ("tex_templates", C.c_uint64), ("minu_big_jobs", C.c_uint64), ("graph_minu_dense_jobs", C.c_uint64),
-                ("graph_tex_dense_jobs", C.c_uint64)]
+                ("graph_tex_dense_jobs", C.c_uint64), ("graph_minu_mid_jobs", C.c_uint64)]
 
 
 _lib = None
@@ -636,7 +636,7 @@ class Matcher:
                 "minu_replays": int(s.minu_replays), "tex_replays": int(s.tex_replays), "tex_queued": int(s.tex_queued),
                 "tex_exact": int(s.tex_exact), "tex_overflow": int(s.tex_overflow), "tex_templates": int(s.tex_templates),
                 "minu_big_jobs": int(s.minu_big_jobs), "graph_minu_dense_jobs": int(s.graph_minu_dense_jobs),
-                "graph_tex_dense_jobs": int(s.graph_tex_dense_jobs)}
+                "graph_tex_dense_jobs": int(s.graph_tex_dense_jobs), "graph_minu_mid_jobs": int(s.graph_minu_mid_jobs)}
 
     def set_streams(self, n: int) -> None:
         """2: texture chain on a second stream (default); 1: all kernels serialised on one stream."""
