@@ -140,6 +140,25 @@ def test_large_images_take_the_dense_graph_kernel(pkg, built, golden, oracle):
     assert st["kernel_launches"] > 0
 
 
+def test_clustered_minutiae_take_the_second_chance_graph_kernel(pkg, built, golden, oracle):
+    """Minutiae concentrated in a small area give distance-consistency graphs far denser than the ~9 % of spread-out
+    impostor prints: they overflow the first sparse graph kernel's 2,560 non-zeros and are retried by
+    graph_minu_mid_kernel (6,656 non-zeros) before anything goes to the dense kernel - same scores bit for bit."""
+    T = pkg.templates
+    cb = golden["codebook"]
+    raws = [T.synth_rolled_raw(5300 + k, n_minu=120) for k in range(8)]
+    rng = np.random.default_rng(5300)
+    for k, r in enumerate(raws):  # sigma of 45..80 px around the centre (uniform over the image otherwise)
+        sig = 45 + 5 * k
+        r.minu.x = np.clip(np.rint(rng.normal(400, sig, r.minu.n)), 0, 799).astype(np.int16)
+        r.minu.y = np.clip(np.rint(rng.normal(384, sig, r.minu.n)), 0, 767).astype(np.int16)
+    rolled = [T.rolled_from_raw(r, cb) for r in raws]
+    latents = [T.synth_latent(97, raws[2]), T.synth_latent(98, raws[6], n_minu=60, n_tex_pts=90)]
+    st = _run(pkg, cb, latents, rolled, oracle)
+    assert st["graph_minu_mid_jobs"] > 0, st
+    assert st["graph_minu_dense_jobs"] < st["graph_minu_mid_jobs"], st  # most of them fit the second chance
+
+
 def test_oversized_minutiae_templates(pkg, built, golden, oracle):
     """Templates beyond the shared-memory tiles of the fast minutiae kernels - up to the reference's own limit of 2000
     minutiae (matcher.cpp:788-841) - run through the HBM-resident kernels of minu_big.cuh: same candidate lists, same
