@@ -338,11 +338,10 @@ typedef struct {
                                        6,656 (clustered minutiae); graph_minu_dense_jobs counts what that left over */
 } lafis_stats;
 LAFIS_API int lafis_get_stats(const lafis_ctx* ctx, lafis_stats* out);
-/* 2 (default): when a match runs in several pipeline chunks the texture chain runs on a second CUDA stream
- * concurrently with the minutiae chain (a single-chunk match keeps both chains on one stream: its kernels are issue-bound
- * and gain nothing from sharing the SMs), and the rare-path kernels (introsort replays, dense texture graphs) run on a
- * third stream next to the following large kernel; 1: every kernel on one stream always - per-kernel times in lafis_stats
- * are then exclusive. */
+/* 2 (default): the rare-path kernels (introsort replays of the selection, dense texture graphs: a few hundred long jobs)
+ * run on a second, high-priority CUDA stream next to the following large kernel of the main stream instead of holding it
+ * up; 1: every kernel on one stream - per-kernel times in lafis_stats are then exclusive.  (Running the whole texture
+ * chain beside the minutiae chain was measured and does not pay; LAFIS_FORCE_TWO_STREAMS=1 re-enables it for experiments.) */
 LAFIS_API int lafis_set_streams(lafis_ctx* ctx, int n_streams);
 LAFIS_API void* lafis_stream(const lafis_ctx* ctx); /* the cudaStream_t all work is enqueued on */
 

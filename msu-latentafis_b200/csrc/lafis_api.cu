@@ -1086,12 +1086,12 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
     }
     c->stage_chunks = n_chunks;
     int chunk_id = 0;
-    // Two streams (texture chain next to the minutiae chain) pay off when the gallery is processed in several chunks,
-    // where one chain's kernels fill the tails of the other's; with a single chunk every kernel is issue-bound on
-    // its own and the overlap only adds contention (measured: 87.3 against 88.3 ms for 1 latent x 100,000 prints in
-    // one chunk, 2,357 against 2,375 ms for 27 latents in ten chunks).
-    static const bool force_two = getenv("LAFIS_FORCE_TWO_STREAMS") != nullptr;  // experiment switch
-    const bool two = c->two_streams && (n_chunks > 1 || force_two);
+    // The texture chain could run on a second stream next to the minutiae chain; it does not pay: the persistent kernels
+    // take whole SMs, and the smaller kernels of the two chains only slow each other down (1 latent x 100,000 prints in one
+    // chunk: 68.7 against 68.1 ms; 27 latents in seven chunks: 1,901 against 1,840 ms; 256 latents x 20,000: 3,630 against
+    // 3,523 ms).  Kept as an experiment switch.
+    static const bool force_two = getenv("LAFIS_FORCE_TWO_STREAMS") != nullptr;
+    const bool two = c->two_streams && force_two;
     cudaStream_t sb = two ? c->stream_b : st;
     // Rare-path kernels on their own (high-priority) stream: the selection's introsort replays run next to the texture
     // graph kernel, the dense texture graphs next to the minutiae graph kernel, instead of a few long jobs holding up the
