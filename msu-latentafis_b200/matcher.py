@@ -639,7 +639,7 @@ class Matcher:
                 "graph_tex_dense_jobs": int(s.graph_tex_dense_jobs), "graph_minu_mid_jobs": int(s.graph_minu_mid_jobs)}
 
     def set_streams(self, n: int) -> None:
-        """2: texture chain on a second stream (default); 1: all kernels serialised on one stream."""
+        """2: rare-path kernels on a second, high-priority stream (default); 1: all kernels serialised on one stream."""
         self._chk(self.L.lafis_set_streams(self.ctx, n))
 
     @property
