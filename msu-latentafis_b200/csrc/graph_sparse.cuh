@@ -416,6 +416,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP, TIER>& w, int num, const float
                 __syncwarp();
             }
             if (!tie_hit) break;
+            __syncwarp();  // every lane is done with the provisional order
             if (lane == 0) std_sort_desc_emulate<float, unsigned short>(w.u.it.b, w.u.it.y, num);
             __syncwarp();
             exact = true;

@@ -245,6 +245,7 @@ struct WarpStdSortEmu {
 
     __device__ bool before(IdxT a, IdxT b) const { return key((int)a) > key((int)b); }
     __device__ void swp(int a, int b) {
+        __syncwarp();  // every lane has read what it decided this swap on
         if (lane == 0) {
             IdxT t = y[a];
             y[a] = y[b];
@@ -310,6 +311,7 @@ struct WarpStdSortEmu {
             if (f.first >= need) continue;
             while (f.last - f.first > 16) {
                 if (f.depth == 0) {
+                    __syncwarp();
                     if (lane == 0) seq.heap_sort(f.first, f.last);
                     __syncwarp();
                     break;
@@ -321,6 +323,7 @@ struct WarpStdSortEmu {
             }
             if (f.last > done_to) done_to = f.last;
         }
+        __syncwarp();
         if (lane == 0) {
             if (n > 16) {
                 int E = done_to;
