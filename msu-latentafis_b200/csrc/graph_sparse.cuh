@@ -12,15 +12,21 @@
 // for ~9 % of the entries (measured: at most 28 of 120 per row).  The reference's dense mat-vec adds
 // H[i][k]*b[k] for k ascending; a zero entry contributes +-0, which leaves an fp32 accumulator
 // unchanged, so summing only the non-zero entries in ascending k is bit-identical and ~10x less work,
-// and the graph fits in ~20 KB of shared memory instead of 57-160 KB: 11 (minutiae) / 4 (texture) CTAs
-// per SM instead of 3 / 1.  Rows are built by one warp each (lanes = columns, ballot compaction keeps
-// ascending column order) into that warp's private slice of a CSR buffer - no atomics.
+// and the graph fits in ~20 KB of shared memory instead of 57-160 KB: 10 (minutiae) / 5 (texture) CTAs
+// per SM instead of 3 / 1.  The graph is built symmetrically from a bit matrix of the pairs a < b that pass a
+// conservative pre-test; the exact entries are computed once per pair and stored at both CSR positions, which
+// follow from popcounts of the bit rows (ascending column order, no sorting).
+//
+// Rankings (candidate order, the texture graph's top-200 rows) come from one bucket pass (block_rank_desc,
+// device_common.cuh); std::sort's permutation inside groups of equal values is replayed only when it can change
+// the outcome (see the greedy pass).
 //
 // The orientation graph runs on the survivors of the first stage (typically < 10) inside ONE warp with
 // the graph as 32-bit row masks; no block barrier after the distance stage.
 //
-// Anything that does not fit - a row slice overflowing (mated pairs have dense graphs) or more than 32
-// survivors - is appended to an overflow list and recomputed from scratch by the dense kernel.
+// Anything that does not fit - a CSR overflowing (clustered minutiae: second chance in graph_minu_mid_kernel;
+// mated pairs have dense graphs) or more than 32 survivors - is appended to an overflow list and recomputed from
+// scratch by the dense kernel.
 #pragma once
 #include "graph_prune.cuh"
 

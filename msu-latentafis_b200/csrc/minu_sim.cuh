@@ -9,23 +9,25 @@
 // oracle/shim/Eigen/Dense).  The gallery's k-major descriptor blocks stream through a double buffer
 // with cp.async while the previous block is being multiplied; the latent's blocks stay resident
 // (single latent) or are re-staged per latent (batches; minu_sim_jobs_kernel stages them once per
-// job instead).  Warp tile 16 x 16*NC, thread tile 8 x NC with NC = 6..10 chosen per template
-// (96..160 columns): per k four loads feed 8*NC multiply-adds.  S goes to HBM ([nL][np] per job) -
+// job instead).  Warp tile 20 x 16*NC, thread tile 10 x NC with NC = 6..10 chosen per template
+// (96..160 columns): per k five loads feed 10*NC multiply-adds.  S goes to HBM ([nL][np] per job) -
 // ~115 KB per pair written once
 // and read once, far below what the path's fp32 issue rate lets HBM see.
 //
-// minu_select_kernel (K6 + K7).  One 384-thread CTA per (latent, template, slot), ~57 KB of shared
-// memory so that four CTAs share an SM and hide each other's barriers.  Column sums (i ascending) and
-// row sums (j ascending) by one thread per column / row over an odd-stride copy of S.  The 120 largest
-// normalised values S/(l_i + r_j - S + 1e-6) are found in two passes over an fp32 estimate of that
-// value (relative error < 1e-6): a 1024-bin histogram of the float bit patterns locates the bin of the
-// 120th value, everything at or above that bin's lower edge (with a 4e-6 relative safety margin, which
-// provably contains the exact top-120) becomes a candidate, and only candidates get the reference's
-// double-precision evaluation (:467).  Candidates are rank-sorted with the total order (value desc,
-// index asc).  If two of the selected values tie, or fewer than 120 values are positive, the
-// permutation libstdc++'s introsort would produce is not implied by the values and the job goes to
-// minu_select_slow_kernel, which evaluates every value in double and replays the introsort
-// (stdsort_emul.h).  The output carries the RAW similarity (:486).
+// minu_select_kernel (K6 + K7).  One 384-thread CTA per (latent, template, slot), ~55 KB of shared
+// memory so that four CTAs share an SM and hide each other's barriers.  S arrives with cp.async into a copy
+// whose row stride is 4 mod 8 floats: rows are 16-byte aligned and 16-byte loads along a row as well as down
+// eight consecutive rows are conflict-free.  Column sums (i ascending) and row sums (j ascending) by one thread
+// per column / row.  The 120 largest normalised values S/(l_i + r_j - S + 1e-6) are found in two passes over an
+// fp32 estimate of that value (relative error < 1e-6), a thread owning one group of four consecutive columns
+// and every RP-th row (its four column sums stay in registers): the K-th largest of the <= 384 thread maxima
+// bounds the K-th largest estimate from below, a 1024-bin histogram of the thread maxima' float bit patterns
+// locates its bin, and everything at or above that bin's lower edge (with a 4e-6 relative safety margin, which
+// provably contains the exact top-120) becomes a candidate; only candidates get the reference's double-precision
+// evaluation (:467).  Candidates are ranked by counting (rank = number of candidates with a larger value).  If
+// two of the selected values tie, or fewer than 120 values are positive, the permutation libstdc++'s introsort
+// would produce is not implied by the values and the job goes to minu_select_slow_kernel, which evaluates every
+// value in double and replays the introsort (stdsort_emul.h).  The output carries the RAW similarity (:486).
 #pragma once
 #include "device_common.cuh"
 #include "minu_plan.h"
