@@ -42,6 +42,8 @@
 // Degenerate rows (all LUT entries ~0) get scale 0 and are evaluated exactly in full, like the rows of a
 // template whose candidate list overflows.
 #pragma once
+#include <type_traits>
+
 #include "device_common.cuh"
 
 namespace lafis {
@@ -218,21 +220,31 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
 
         // ---- quantised LUT of rows [rt*32, rt*32+32) ----
         const size_t row0 = (size_t)q * P.lt_stride + (size_t)rt * kRowTile;
-        if (tid < kRowTile) s_scale[tid] = (rt * kRowTile + tid < P.lt_stride) ? P.row_scale[row0 + tid] : -1.0f;
+        // A tile with at most 16 live rows (the last one of a latent: 400 texture points are 12.5 tiles) runs in HALF
+        // mode: the 16 rows are laid into both halves of the LUT, and the two lanes of a pair - which otherwise share a
+        // rolled point and split the 32 rows - take a rolled point each, 32 per batch instead of 16.  Same gathers, same
+        // conflict-free pattern (a phase's eight lanes still hit the eight 16-byte groups of their 128-byte lines), half
+        // the batches: the tile costs half instead of a full tile's time for half a tile's rows.
+        const bool half = nLt - rt * kRowTile <= kRowTile / 2;
+        const int src_of_slot = half ? (tid & 15) : tid;  // LUT slot -> row of the tile
+        if (tid < kRowTile) s_scale[tid] = (rt * kRowTile + src_of_slot < P.lt_stride) ? P.row_scale[row0 + src_of_slot] : -1.0f;
         __syncthreads();
-        // a thread quantises 16 rows of one (sub-quantizer, code) and stores them as one 16-byte vector
+        // a thread quantises 16 rows of one (sub-quantizer, code) and stores them as one 16-byte vector; four iterations'
+        // 64 loads (L2) in flight per thread: the build is ~3 % of the kernel and latency-bound
+#pragma unroll 4
         for (int e = tid; e < 2 * 4096; e += kRowmaxThreads) {
-            const int mc = e & 4095, half = e >> 12;
+            const int mc = e & 4095, hslot = e >> 12;
             const int m = mc >> 8, code = mc & 255;
             uint32_t wv[4] = {0u, 0u, 0u, 0u};
+            const float* src = P.lut + (row0 + (size_t)(half ? 0 : hslot * 16)) * 4096 + mc;  // half mode: both halves hold rows 0..15
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const float sc = s_scale[half * 16 + r];
+                const float sc = s_scale[hslot * 16 + r];
                 uint32_t qv = 0;
-                if (sc > 0.0f) qv = (uint32_t)min((int)rintf(f_mul(__ldg(P.lut + (row0 + half * 16 + r) * 4096 + mc), sc)), kQLevels);
+                if (sc > 0.0f) qv = (uint32_t)min((int)rintf(f_mul(__ldg(src + (size_t)r * 4096), sc)), kQLevels);
                 wv[r >> 2] |= qv << (8 * (r & 3));
             }
-            *reinterpret_cast<uint4*>(lut8 + (((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + half * 16) =
+            *reinterpret_cast<uint4*>(lut8 + (((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + hslot * 16) =
                 make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
         __syncthreads();
@@ -244,7 +256,14 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
             if (sc > 0.0f) row_live |= 1u << r;
             if (sc == 0.0f) row_degen |= 1u << r;
         }
-        const uint32_t degen_all = __shfl_sync(0xffffffffu, row_degen, 0) | (__shfl_sync(0xffffffffu, row_degen, 1) << 16);
+        const uint32_t degen_all =
+            half ? __shfl_sync(0xffffffffu, row_degen, 0)
+                 : __shfl_sync(0xffffffffu, row_degen, 0) | (__shfl_sync(0xffffffffu, row_degen, 1) << 16);
+        // rolled points per batch and this lane's point inside a batch; the lanes that hold the same rows
+        const int cpb = half ? 32 : 16;
+        const int jcol = half ? 2 * jl + hf : jl;
+        const unsigned row_mask = half ? 0xffffffffu : hf_mask;
+        const uint32_t slot_mask = half ? 0xffffu : 0xffffffffu;  // LUT slots that stand for rows of the tile
 
         // ---- stream the slice: warps draw templates from a shared counter (template sizes vary 600..1000 points) ----
         const int t_begin = slice * slice_len;
@@ -274,7 +293,7 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
             if (n <= 0) continue;
             ++n_tpl;
             ws.best[lane] = 0ull;
-            const uint4* cp = P.codes + base + jl;
+            const uint4* cp = P.codes + base + jcol;
 
             // per (lane, row): the two smallest tracking fields of this lane's columns, as packed 16-bit fields
             // (Dq >> 2) << 6 | batch: 10 bits of distance (Dq <= 4080), 6 bits of batch index (<= 62)
@@ -284,13 +303,15 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
 
             // code words two batches ahead: wherever ptxas places the load inside the body, a full batch of work
             // lies between it and its first use
+            auto stream = [&](auto cpb_tag) {
+            constexpr int CPB = decltype(cpb_tag)::value;  // rolled points per batch: 16, or 32 in half mode
             uint4 cnext = __ldg(cp), cnext2 = cnext;
-            if (16 < n) cnext2 = __ldg(cp + 16);
+            if (CPB < n) cnext2 = __ldg(cp + CPB);
             uint32_t bp = 0;  // batch index in both fields
-            for (int j0 = 0; j0 < n; j0 += 16, bp += 0x00010001u) {
+            for (int j0 = 0; j0 < n; j0 += CPB, bp += 0x00010001u) {
                 const uint4 c = cnext;
                 cnext = cnext2;
-                if (j0 + 32 < n) cnext2 = __ldg(cp + j0 + 32);
+                if (j0 + 2 * CPB < n) cnext2 = __ldg(cp + j0 + 2 * CPB);
                 // The integer ALU pipe (PRMT, IADD3, VIMNMX: 16 lanes/clk per scheduler) would bound this loop, so the
                 // additions go to the FMA pipe (IMAD with a run-time multiplier of 1); the two pipes end up level.
                 uint32_t all[4] = {0u, 0u, 0u, 0u}, odd[4] = {0u, 0u, 0u, 0u};
@@ -314,7 +335,7 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                         }
                     }
                 }
-                if (j0 + jl < n) {
+                if (j0 + jcol < n) {
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
                         const uint32_t dq[2] = {all[w] - (odd[w] << 8), odd[w]};  // rows 4w | 4w+2, rows 4w+1 | 4w+3
@@ -329,6 +350,9 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                     }
                 }
             }
+            };
+            if (half) stream(std::integral_constant<int, 32>{});
+            else stream(std::integral_constant<int, 16>{});
 
             // ---- candidates: columns whose quantised distance is within kWindow of the row minimum ----
             int cnt = 0, acnt = 0;
@@ -339,22 +363,22 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                 const uint32_t second = (f & 1) ? (f2[f >> 1] >> 16) : (f2[f >> 1] & 0xffffu);
                 const uint32_t third = (f & 1) ? (f3[f >> 1] >> 16) : (f3[f >> 1] & 0xffffu);
                 // Dq_j <= Dq_min + kWindow  =>  (Dq_j >> 2) <= (Dq_min >> 2) + kWindowQ
-                const uint32_t limq = (__reduce_min_sync(hf_mask, mine) >> 6) + kWindowQ;
+                const uint32_t limq = (__reduce_min_sync(row_mask, mine) >> 6) + kWindowQ;
                 const bool live = (row_live >> rl) & 1u;
                 const bool amb = live && (third >> 6) <= limq;                 // >= 3 of my columns inside the window: re-scan
                 const bool cand = live && !amb && (mine >> 6) <= limq;         // my best column
                 const bool cand2 = cand && (second >> 6) <= limq;              // and my second best
                 const unsigned mc = __ballot_sync(0xffffffffu, cand), mc2 = __ballot_sync(0xffffffffu, cand2);
                 const unsigned ma = __ballot_sync(0xffffffffu, amb);
-                const int row = hf * 16 + rl;
+                const int row = half ? rl : hf * 16 + rl;
                 if (cand) {
                     const int pos = cnt + __popc(mc & lt_mask);
-                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(16 * (int)(mine & 63u) + jl) << 5);
+                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(cpb * (int)(mine & 63u) + jcol) << 5);
                 }
                 cnt += __popc(mc);
                 if (cand2) {
                     const int pos = cnt + __popc(mc2 & lt_mask);
-                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(16 * (int)(second & 63u) + jl) << 5);
+                    if (pos < kCandCap) ws.cand[pos] = (uint32_t)row | ((uint32_t)(cpb * (int)(second & 63u) + jcol) << 5);
                 }
                 cnt += __popc(mc2);
                 if (amb) {
@@ -371,8 +395,9 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                 const int row = (int)(ent & 31u), al = (int)((ent >> 5) & 31u);
                 const uint32_t lim = ent >> 10;
                 const int ajl = (al >> 3) * 4 + ((al >> 1) & 3);
-                for (int b0 = 0; b0 * 16 < n; b0 += 32) {
-                    const int j = (b0 + lane) * 16 + ajl;
+                const int ajcol = half ? 2 * ajl + (al & 1) : ajl;
+                for (int b0 = 0; b0 * cpb < n; b0 += 32) {
+                    const int j = (b0 + lane) * cpb + ajcol;
                     bool hit = false;
                     if (j < n) hit = (tex_quant_dist(lut8, row, __ldg(P.codes + base + j)) >> 2) <= lim;
                     const unsigned mh = __ballot_sync(0xffffffffu, hit);
@@ -391,7 +416,7 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
             uint32_t full = degen_all;  // rows evaluated in full
             if (overflow) {
                 ++n_over;
-                full = 0xffffffffu;
+                full = slot_mask;
             } else {
                 n_cand += (lane == 0) ? cnt : 0;
                 for (int e = lane; e < cnt; e += 32) {
@@ -413,7 +438,7 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
                 }
             }
             __syncwarp();
-            if (s_scale[lane] >= 0.0f) {
+            if (((slot_mask >> lane) & 1u) && s_scale[lane] >= 0.0f) {
                 const unsigned long long k = ws.best[lane];
                 uint32_t u = (uint32_t)(k >> 32);
                 u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
