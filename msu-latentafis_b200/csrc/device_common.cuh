@@ -209,6 +209,7 @@ __device__ __forceinline__ void block_rank_desc(const uint32_t (&u)[KPT], int n,
             const int base = start[bin[e] + 1], cnt = start[bin[e]] - base;
             const uint32_t id = (uint32_t)(tid + e * NT);
             int gt = 0, before = 0;
+#pragma unroll 1
             for (int p = 0; p < cnt; ++p) {
                 const uint2 o = buck[base + p];
                 gt += o.x > u[e];

@@ -312,6 +312,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP, TIER>& w, int num, const float
         if (tid < num) {
             const int rs = w.row_start[tid], len = w.row_len[tid];
             float acc = 0.0f;
+#pragma unroll 2
             for (int e = 0; e < len; ++e) acc = f_add(acc, f_mul(w.vals[rs + e], w.u.it.b[w.cols[rs + e]]));
             w.u.it.c[tid] = acc;
         }
