@@ -329,6 +329,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP, TIER>& w, int num, const float
                     v = c4[i >> 2];
                     sum = f_add(f_add(f_add(f_add(sum, v.x), v.y), v.z), v.w);
                 }
+#pragma unroll 1
                 for (; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
             } else {
                 for (int i = 1; i < num; ++i) sum = f_add(sum, w.u.it.c[i]);
@@ -380,6 +381,7 @@ __device__ bool sparse_cascade(SparseWork<LOOKUP, TIER>& w, int num, const float
                 bv[c] = (p < num) ? w.u.it.b[ind[c]] : 0.0f;
                 if (p < num && !((double)bv[c] < 0.0001)) open |= 1u << c;
             }
+#pragma unroll 1
             for (int c = lane; c < P2; c += 32) w.mark[c] = 0;
             __syncwarp();
             bool tie_hit = false;
@@ -535,6 +537,7 @@ __device__ __forceinline__ void graph_minu_job(SparseWork<false, TIER>& w, const
         w.tie = 0;
         w.npairs = 0;
     }
+#pragma unroll 1
     for (int e = tid; e < G::MAXP * G::NCH; e += G::NT) (&w.u.M[0][0])[e] = 0u;
     int big = 0;
     if (tid < num) {
