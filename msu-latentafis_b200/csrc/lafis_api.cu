@@ -215,6 +215,7 @@ void lafis_destroy(lafis_ctx* c) {
     c->rowmax_val.release();
     c->tex_lut.release();
     c->tex_scale.release();
+    c->tex_lut8.release();
     c->rowmax_j.release();
     c->corr_v.release();
     c->corr_ij.release();
@@ -1063,6 +1064,7 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
 
     LAFIS_CUDA(c, c->tex_lut.reserve((size_t)Q * lt * 4096));
     LAFIS_CUDA(c, c->tex_scale.reserve((size_t)Q * lt));
+    LAFIS_CUDA(c, c->tex_lut8.reserve((size_t)Q * ((lt + kRowTile - 1) / kRowTile) * kLutBytes));
     LAFIS_CUDA(c, c->rowmax_val.reserve((size_t)Q * n_chunk_max * lt));
     LAFIS_CUDA(c, c->rowmax_j.reserve((size_t)Q * n_chunk_max * lt));
     LAFIS_CUDA(c, c->corr_v.reserve((size_t)Q * n_chunk_max * 3 * kTopCorrMinu));
@@ -1117,7 +1119,16 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
         P.lut = c->tex_lut.p;
         P.row_scale = c->tex_scale.p;
         tex_lut_kernel<<<dim3(L->lt_stride, Q), 256, 0, sb>>>(P);
-        c->stats.kernel_launches += 1;
+        // ... and their 8-bit copies, one 128 KB tile per 32 rows in the layout tex_rowmax_kernel gathers from
+        TexRowmaxParams T;
+        T.lut = c->tex_lut.p;
+        T.row_scale = c->tex_scale.p;
+        T.lut8 = c->tex_lut8.p;
+        T.lat_nt = D.tex_n;
+        T.lt_stride = L->lt_stride;
+        T.Q = Q;
+        tex_lut8_kernel<<<dim3((L->lt_stride + kRowTile - 1) / kRowTile, Q), 512, 0, sb>>>(T);
+        c->stats.kernel_launches += 2;
     }
     for (int g0 = 0; g0 < G; g0 += n_chunk_max) {
         const int n_chunk = std::min(n_chunk_max, G - g0);
@@ -1241,6 +1252,7 @@ int lafis::run_match(lafis_ctx* c, lafis_latents* L, int topk) {
             TexRowmaxParams P;
             P.lut = c->tex_lut.p;
             P.row_scale = c->tex_scale.p;
+            P.lut8 = c->tex_lut8.p;
             P.lat_nt = D.tex_n;
             P.lt_stride = L->lt_stride;
             P.Q = Q;

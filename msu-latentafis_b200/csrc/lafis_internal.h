@@ -130,6 +130,7 @@ struct lafis_ctx {
 
     // work buffers
     lafis::DevBuf<float> tex_lut, tex_scale;  // fp32 PQ distance tables of the latent batch (K1) + per-row quantiser scales
+    lafis::DevBuf<unsigned char> tex_lut8;    // the row tiles' 8-bit tables in tex_rowmax_kernel's shared-memory layout (128 KB per 32 rows)
     lafis::DevBuf<float> rowmax_val;
     lafis::DevBuf<uint16_t> rowmax_j;
     lafis::DevBuf<float> corr_v;

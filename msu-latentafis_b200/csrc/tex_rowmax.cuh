@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) tex_lut_kernel(TexLutParams P) {
 struct TexRowmaxParams {
     const float* lut;          // [Q][lt_stride][16][256] fp32, exact
     const float* row_scale;    // [Q][lt_stride]; < 0 for padding rows
+    unsigned char* lut8;       // [Q][row tiles][kLutBytes]: the tiles' 8-bit tables as the kernel holds them (tex_lut8_kernel)
     const int* lat_nt;         // [Q]
     int lt_stride;
     int Q;
@@ -169,6 +170,39 @@ __device__ __forceinline__ uint32_t tex_quant_dist(const unsigned char* __restri
             d += lut8[((s * 256 + code) * 4 + b) * kRowTile + row];
         }
     return d;
+}
+
+// The 8-bit table of one (latent, 32-row tile) in the layout tex_rowmax_kernel gathers from, [s][code][b][row] (sub-quantizer
+// m = 4s + b): q = min(rint(LUT * scale), 255) per row, 0 for rows that are not quantised (padding, degenerate).  A tile with
+// at most 16 live rows is laid out for the kernel's half mode: both 16-row halves hold rows 0..15.
+__global__ void __launch_bounds__(512) tex_lut8_kernel(TexRowmaxParams P) {
+    const int rt = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+    const int nLt = P.lat_nt[q];
+    if (rt * kRowTile >= nLt) return;
+    __shared__ float s_scale[kRowTile];
+    const int n_rowtiles = (P.lt_stride + kRowTile - 1) / kRowTile;
+    const size_t row0 = (size_t)q * P.lt_stride + (size_t)rt * kRowTile;
+    const bool half = nLt - rt * kRowTile <= kRowTile / 2;
+    const int src_of_slot = half ? (tid & 15) : tid;  // LUT slot -> row of the tile
+    if (tid < kRowTile) s_scale[tid] = (rt * kRowTile + src_of_slot < P.lt_stride) ? P.row_scale[row0 + src_of_slot] : -1.0f;
+    __syncthreads();
+    unsigned char* out = P.lut8 + ((size_t)q * n_rowtiles + rt) * kLutBytes;
+    // a thread quantises 16 rows of one (sub-quantizer, code) and stores them as one 16-byte vector
+    for (int e = tid; e < 2 * 4096; e += 512) {
+        const int mc = e & 4095, hslot = e >> 12;
+        const int m = mc >> 8, code = mc & 255;
+        uint32_t wv[4] = {0u, 0u, 0u, 0u};
+        const float* src = P.lut + (row0 + (size_t)(half ? 0 : hslot * 16)) * 4096 + mc;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float sc = s_scale[hslot * 16 + r];
+            uint32_t qv = 0;
+            if (sc > 0.0f) qv = (uint32_t)min((int)rintf(f_mul(__ldg(src + (size_t)r * 4096), sc)), kQLevels);
+            wv[r >> 2] |= qv << (8 * (r & 3));
+        }
+        *reinterpret_cast<uint4*>(out + (((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + hslot * 16) =
+            make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
 }
 
 __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
@@ -229,23 +263,13 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
         const int src_of_slot = half ? (tid & 15) : tid;  // LUT slot -> row of the tile
         if (tid < kRowTile) s_scale[tid] = (rt * kRowTile + src_of_slot < P.lt_stride) ? P.row_scale[row0 + src_of_slot] : -1.0f;
         __syncthreads();
-        // a thread quantises 16 rows of one (sub-quantizer, code) and stores them as one 16-byte vector; four iterations'
-        // 64 loads (L2) in flight per thread: the build is ~3 % of the kernel and latency-bound
-#pragma unroll 4
-        for (int e = tid; e < 2 * 4096; e += kRowmaxThreads) {
-            const int mc = e & 4095, hslot = e >> 12;
-            const int m = mc >> 8, code = mc & 255;
-            uint32_t wv[4] = {0u, 0u, 0u, 0u};
-            const float* src = P.lut + (row0 + (size_t)(half ? 0 : hslot * 16)) * 4096 + mc;  // half mode: both halves hold rows 0..15
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const float sc = s_scale[hslot * 16 + r];
-                uint32_t qv = 0;
-                if (sc > 0.0f) qv = (uint32_t)min((int)rintf(f_mul(__ldg(src + (size_t)r * 4096), sc)), kQLevels);
-                wv[r >> 2] |= qv << (8 * (r & 3));
-            }
-            *reinterpret_cast<uint4*>(lut8 + (((m >> 2) * 256 + code) * 4 + (m & 3)) * kRowTile + hslot * 16) =
-                make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        {   // the tile's 8-bit table, quantised once per match by tex_lut8_kernel: 128 KB from L2 (a per-job build from the
+            // fp32 table took ~25 us, 2.7 % of this kernel at two slices per SM).  Plain 16-byte loads, eight in flight:
+            // the form of this copy decides which schedule ptxas finds for the stream loop below (cp.async or other
+            // unroll factors: 24.7 ms against 24.2 ms, tools/run_variants.sh on one box).
+            const uint4* src = reinterpret_cast<const uint4*>(P.lut8 + ((size_t)q * n_rowtiles + rt) * kLutBytes);
+#pragma unroll 8
+            for (int e = tid; e < kLutBytes / 16; e += kRowmaxThreads) reinterpret_cast<uint4*>(lut8)[e] = __ldg(src + e);
         }
         __syncthreads();
         // rows of this lane's half: live (take part), degenerate (scale 0: every column is a candidate)
