@@ -317,11 +317,12 @@ typedef struct {
     uint64_t kernel_launches; /* kernels launched by this library since the context was created */
     uint64_t pairs_scored;    /* (latent, gallery) pairs scored */
     float last_match_ms;      /* device time of the last lafis_match*, CUDA events */
-    float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events between the
-                                 launches): 0 tex_rowmax, 1 minu_sim, 2 minu_select, 3 graph_minu_sparse,
-                                 4 graph_tex (sparse + dense), 5 fuse + rank lists, 6 minu_select_slow (+ the oversized-pair kernels),
-                                 7 graph_minu_dense.  The texture chain (0, 4) runs on a second stream
-                                 concurrently with the others, so the intervals overlap. */
+    float last_stage_ms[8];   /* per-kernel device times of the last match (CUDA events around the launches):
+                                 0 tex_rowmax, 1 minu_sim, 2 minu_select, 3 graph_minu_sparse, 4 graph_tex (sparse +
+                                 dense), 5 fuse + rank lists, 6 minu_select_slow (+ the oversized-pair kernels),
+                                 7 graph_minu second chance + dense.  With the default two streams the rare-path kernels
+                                 (6 and the dense part of 4) overlap the large kernels; lafis_set_streams(ctx, 1) makes
+                                 the intervals exclusive. */
     /* cumulative exactness bookkeeping since the context was created */
     uint64_t minu_replays;    /* top-120 selections that needed the introsort replay (ties) */
     uint64_t tex_replays;     /* top-200 row selections that needed the introsort replay */
