@@ -209,7 +209,6 @@ __global__ void __maxnreg__(kRowmaxRegs) tex_rowmax_kernel(TexRowmaxParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* lut8 = smem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kRowmaxThreads / 32;
     TexWarpState& ws = reinterpret_cast<TexWarpState*>(smem + kLutBytes)[warp];
     __shared__ int s_job, s_next;
     __shared__ float s_scale[kRowTile];
